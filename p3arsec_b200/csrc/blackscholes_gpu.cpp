@@ -1,0 +1,197 @@
+/*
+ * blackscholes_gpu.cpp -- drop-in driver:  blackscholes_gpu <nthreads> <inputFile> <outputFile>
+ *
+ * Keeps the surface of the reference driver main()
+ * (/root/reference/parsec-ff/pkgs/apps/blackscholes/src/blackscholes.c:664-960): the three positional
+ * arguments (:686-693), the stdout banner and "Num of Options / Num of Runs / Size of data" lines
+ * (:676-680,:744-745,:769), the input grammar and error strings (:696-739), NUM_RUNS repetitions inside
+ * the ROI (:87,:318), the "%.18f" prices file (:923-947) and, when built with -DERR_CHK, the
+ * "Error on ..." / "Num Errors" lines (:333-340,:949-951).  What changes is what north_star names:
+ * rows are parsed by all host cores straight into pinned SoA buffers (no AoS array), the Map runs on
+ * the GPUs through the C ABI of include/bs_gpu.h, and <nthreads> selects the number of GPUs (clamped
+ * to the devices present) instead of the number of host worker threads.
+ *
+ * Build switches mirror the reference's: -DERR_CHK (src/Makefile:53-55), -DBS_FPTYPE=double instead of
+ * editing `#define fptype` (:85), -DNUM_RUNS=<n> (:87).
+ */
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "bs_gpu.h"
+#include "bs_io.h"
+
+#ifndef BS_FPTYPE
+#define BS_FPTYPE float
+#endif
+#define fptype BS_FPTYPE
+
+#ifndef NUM_RUNS
+#define NUM_RUNS 100
+#endif
+
+/* Only for "Size of data": the reference's AoS record (blackscholes.c:89-100).  Never instantiated. */
+typedef struct OptionData_ {
+    fptype s, strike, r, divq, v, t;
+    char OptionType;
+    fptype divs, DGrefval;
+} OptionData;
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char **argv)
+{
+    const double t_begin = now_s();
+#ifdef PARSEC_VERSION
+#define BS_STR2(x) #x
+#define BS_STR(x) BS_STR2(x)
+    printf("PARSEC Benchmark Suite Version " BS_STR(PARSEC_VERSION) "\n");
+#else
+    printf("PARSEC Benchmark Suite\n");
+#endif
+    fflush(NULL);
+
+    if (argc != 4) {
+        printf("Usage:\n\t%s <nthreads> <inputFile> <outputFile>\n", argv[0]);
+        exit(1);
+    }
+    int nThreads = atoi(argv[1]);
+    const char *inputFile = argv[2];
+    const char *outputFile = argv[3];
+
+    // Read input data from file
+    bs_io_file *in = NULL;
+    long long header = 0;
+    int rv = bs_io_open(inputFile, &in, &header);
+    if (rv == BS_IO_ERR_OPEN) {
+        printf("ERROR: Unable to open file `%s'.\n", inputFile);
+        exit(1);
+    }
+    if (rv != BS_IO_OK) {
+        printf("ERROR: Unable to read from file `%s'.\n", inputFile);
+        exit(1);
+    }
+    int numOptions = (int)header;
+    if (nThreads > numOptions) {
+        printf("WARNING: Not enough work, reducing number of threads to match number of options.\n");
+        nThreads = numOptions;
+    }
+    if (numOptions < 0) {
+        printf("ERROR: Unable to read from file `%s'.\n", inputFile);
+        exit(1);
+    }
+
+    // <nthreads> -> number of GPUs
+    const int have = bs_gpu_device_count();
+    if (have <= 0) {
+        printf("ERROR: no usable CUDA device (this build has no CPU path).\n");
+        exit(1);
+    }
+    int nGpus = nThreads < 1 ? 1 : nThreads;
+    if (nGpus > have) nGpus = have;
+
+    bs_gpu_ctx *ctx = NULL;
+    rv = bs_gpu_init(&ctx, nGpus, (size_t)numOptions, (int)sizeof(fptype));
+    if (rv != BS_GPU_OK) {
+        printf("ERROR: bs_gpu_init failed: %s.\n", bs_gpu_status_string(rv));
+        exit(1);
+    }
+
+    // The SoA arrays of the reference (blackscholes.c:102-111), here views of pinned host memory.
+    fptype *sptprice = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_SPTPRICE);
+    fptype *strike = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_STRIKE);
+    fptype *rate = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_RATE);
+    fptype *volatility = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_VOLATILITY);
+    fptype *otime = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_OTIME);
+    int *otype = (int *)bs_gpu_host_buffer(ctx, BS_BUF_OTYPE);
+    fptype *prices = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_PRICES);
+    fptype *dgrefval = (fptype *)bs_gpu_host_buffer(ctx, BS_BUF_DGREFVAL);
+
+    rv = bs_io_load(in, (int)sizeof(fptype), (size_t)numOptions, sptprice, strike, rate, volatility, otime, otype,
+                    dgrefval, NULL, NULL, 0);
+    if (rv != BS_IO_OK) {
+        printf("ERROR: Unable to read from file `%s'.\n", inputFile);
+        exit(1);
+    }
+    rv = bs_io_close(in);
+    if (rv != BS_IO_OK) {
+        printf("ERROR: Unable to close file `%s'.\n", inputFile);
+        exit(1);
+    }
+    const double t_loaded = now_s();
+
+    printf("Num of Options: %d\n", numOptions);
+    printf("Num of Runs: %d\n", NUM_RUNS);
+    printf("Size of data: %d\n", (int)(numOptions * (sizeof(OptionData) + sizeof(int))));
+
+    // ---- ROI (blackscholes.c:781-914).  Here it spans H2D + NUM_RUNS kernel launches + D2H. ----
+    printf("[HOOKS] Entering ROI\n");
+    fflush(NULL);
+    const double t_roi0 = now_s();
+    unsigned long long numError = 0;
+#ifdef ERR_CHK
+    const int err_chk = 1;
+#else
+    const int err_chk = 0;
+#endif
+    rv = bs_gpu_price(ctx, NUM_RUNS, err_chk, &numError);
+    const double t_roi1 = now_s();
+    if (rv != BS_GPU_OK) {
+        printf("ERROR: bs_gpu_price failed: %s (%s).\n", bs_gpu_status_string(rv), bs_gpu_last_error(ctx));
+        exit(1);
+    }
+    bs_gpu_timing tm;
+    bs_gpu_get_timing(ctx, &tm);
+    printf("roi.time|%.9f\n", t_roi1 - t_roi0);
+    printf("[HOOKS] Leaving ROI\n");
+    printf("[BS_GPU] gpus=%d h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f launches=%llu\n", nGpus, tm.h2d_ms, tm.roi_ms,
+           tm.d2h_ms, tm.kernel_launches);
+    if (tm.roi_ms > 0)
+        printf("[BS_GPU] kernel-only rate: %.3f G options/s\n", (double)numOptions * NUM_RUNS / (tm.roi_ms * 1e-3) / 1e9);
+
+#ifdef ERR_CHK
+    {
+        // The reference prints every offender once per run, in index order for one worker.
+        long long *bad = (long long *)malloc(sizeof(long long) * BS_GPU_MAX_ERROR_LIST);
+        const long long nbad = bs_gpu_errors(ctx, bad, BS_GPU_MAX_ERROR_LIST);
+        for (int j = 0; j < NUM_RUNS; j++)
+            for (long long e = 0; e < nbad; e++) {
+                const long long i = bad[e];
+                const fptype price = prices[i];
+                const fptype priceDelta = dgrefval[i] - price;
+                printf("Error on %d. Computed=%.5f, Ref=%.5f, Delta=%.5f\n", (int)i, price, dgrefval[i], priceDelta);
+            }
+        free(bad);
+    }
+#endif
+
+    // Write prices to output file
+    const double t_w0 = now_s();
+    rv = bs_io_write_prices(outputFile, (int)sizeof(fptype), (size_t)numOptions, prices, 0);
+    if (rv == BS_IO_ERR_OPEN) {
+        printf("ERROR: Unable to open file `%s'.\n", outputFile);
+        exit(1);
+    }
+    if (rv == BS_IO_ERR_CLOSE) {
+        printf("ERROR: Unable to close file `%s'.\n", outputFile);
+        exit(1);
+    }
+    if (rv != BS_IO_OK) {
+        printf("ERROR: Unable to write to file `%s'.\n", outputFile);
+        exit(1);
+    }
+    const double t_w1 = now_s();
+
+#ifdef ERR_CHK
+    printf("Num Errors: %d\n", (int)numError);
+#endif
+    bs_gpu_fini(ctx);
+    printf("[BS_GPU] load_s=%.3f write_s=%.3f total_s=%.3f\n", t_loaded - t_begin, t_w1 - t_w0, now_s() - t_begin);
+    printf("[HOOKS] Total time spent in ROI: %.3fs\n", t_roi1 - t_roi0);
+    printf("[HOOKS] Terminating\n");
+    return 0;
+}

@@ -1,0 +1,793 @@
+/*
+ * bs_gpu.cu -- implementation of the C ABI in include/bs_gpu.h (libbs_gpu.so).
+ *
+ * Host-side structure (north_star item 3): one host thread per device.  Each thread binds its device
+ * once, owns that device's stream, events, CUDA graphs and its contiguous shard of the option range,
+ * and executes commands (upload / run / download / fill) posted by the caller thread; a command is
+ * complete when every device thread has finished it.  There is no inter-device traffic: shards are
+ * independent, exactly like the worker ranges of the reference's static parallel-for
+ * (/root/reference/parsec-ff/pkgs/libs/fastflow/ff/parallel_for_internals.hpp:498-518).
+ *
+ * Device memory layout (per shard, count = options in the shard): ONE cudaMalloc arena holding
+ *   [sptprice | strike | rate | volatility | otime | otype | prices | DGrefval]
+ * each stream padded to a multiple of 256 bytes so that every stream base is 256-byte aligned and all
+ * 128-bit vector accesses of the kernel are aligned whatever `count` is.  (The reference packs the five
+ * fp streams back to back without padding, blackscholes.c:750-755, which would misalign them for
+ * count % 4 != 0.)
+ */
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/bs_gpu.h"
+#include "bs_kernels.cuh"
+#include "bs_option_table.h"
+
+namespace {
+
+enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_FILL, CMD_TEARDOWN, CMD_EXIT };
+
+struct GraphKey {
+    int num_runs, err_chk;
+    bool operator<(const GraphKey &o) const { return num_runs != o.num_runs ? num_runs < o.num_runs : err_chk < o.err_chk; }
+};
+
+struct Shard {
+    int index = 0;
+    int device = 0;
+    size_t first = 0, count = 0;
+    int sm_count = 0;
+    // device memory
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    void *d[BS_BUF_COUNT] = {nullptr};
+    unsigned long long *d_err_count = nullptr;
+    unsigned int *d_list_count = nullptr;
+    long long *d_list = nullptr;
+    char *d_table = nullptr;  // synthetic base table, built on first fill
+    // execution
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    int threads = 0, blocks = 0;
+    // results of the last command
+    int status = BS_GPU_OK;
+    std::string err;
+    float h2d_ms = 0, roi_ms = 0, d2h_ms = 0;
+    unsigned long long err_total = 0;
+    unsigned int list_n = 0;
+    std::vector<long long> list;
+    bool refval_on_device = false;
+    std::thread worker;
+};
+
+}  // namespace
+
+struct bs_gpu_ctx {
+    size_t n = 0;
+    int fp_bytes = 4;
+    unsigned flags = 0;
+    int math = BS_MATH_FAST;
+    int cfg_threads = 0, cfg_blocks_per_sm = 0, unroll = 0, variant = 0;
+    std::vector<Shard> shards;
+    void *host[BS_BUF_COUNT] = {nullptr};
+    bool inputs_dirty = true;   // host inputs newer than device copy
+    bool device_valid = false;  // device inputs hold something meaningful
+    // command mailbox
+    std::mutex mu;
+    std::condition_variable cv_cmd, cv_done;
+    unsigned long long epoch = 0;
+    int cmd = CMD_NONE;
+    int pending = 0;
+    // command arguments
+    int arg_num_runs = 0, arg_err_chk = 0, arg_upload_what = 0;
+    unsigned long long arg_first_index = 0;
+    // reporting
+    bs_gpu_timing timing;
+    std::string err;
+    bs_gpu_ctx() { memset(&timing, 0, sizeof(timing)); }
+};
+
+namespace {
+
+size_t elem_bytes(const bs_gpu_ctx *c, int which) { return which == BS_BUF_OTYPE ? sizeof(int) : (size_t)c->fp_bytes; }
+size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+void set_err(Shard &s, int status, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    s.status = status;
+    s.err = buf;
+}
+
+#define SH_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_err(s, e_ == cudaErrorMemoryAllocation ? BS_GPU_ERR_NOMEM : BS_GPU_ERR_CUDA,            \
+                    "device %d: %s failed: %s", s.device, #call, cudaGetErrorString(e_));               \
+            return;                                                                                     \
+        }                                                                                               \
+    } while (0)
+
+// ---- kernel dispatch -----------------------------------------------------------------------------
+typedef void (*KernelF32)(bsk::StreamsF32, size_t, bsk::ErrChk);
+typedef void (*KernelF64)(bsk::StreamsF64, size_t, bsk::ErrChk);
+
+template <int MATH, bool CHK>
+KernelF32 pick_f32_unroll(int unroll)
+{
+    switch (unroll) {
+    case 1: return bsk::bs_map_f32<MATH, 1, CHK>;
+    case 4: return bsk::bs_map_f32<MATH, 4, CHK>;
+    default: return bsk::bs_map_f32<MATH, 2, CHK>;
+    }
+}
+KernelF32 pick_f32(int math, int unroll, bool chk)
+{
+    if (math == BS_MATH_IEEE) return chk ? pick_f32_unroll<bsk::MATH_IEEE, true>(unroll) : pick_f32_unroll<bsk::MATH_IEEE, false>(unroll);
+    return chk ? pick_f32_unroll<bsk::MATH_FAST, true>(unroll) : pick_f32_unroll<bsk::MATH_FAST, false>(unroll);
+}
+KernelF64 pick_f64(int unroll, bool chk)
+{
+    switch (unroll) {
+    case 1: return chk ? bsk::bs_map_f64<1, true> : bsk::bs_map_f64<1, false>;
+    case 4: return chk ? bsk::bs_map_f64<4, true> : bsk::bs_map_f64<4, false>;
+    default: return chk ? bsk::bs_map_f64<2, true> : bsk::bs_map_f64<2, false>;
+    }
+}
+const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
+{
+    return c->fp_bytes == 4 ? (const void *)pick_f32(c->math, c->unroll, chk) : (const void *)pick_f64(c->unroll, chk);
+}
+
+void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record)
+{
+    bsk::ErrChk ec;
+    ec.count = s.d_err_count;
+    ec.list_count = s.d_list_count;
+    ec.list = s.d_list;
+    ec.list_cap = BS_GPU_MAX_ERROR_LIST;
+    ec.record = record;
+    if (c->fp_bytes == 4) {
+        bsk::StreamsF32 a;
+        a.spt = (const float *)s.d[BS_BUF_SPTPRICE];
+        a.strike = (const float *)s.d[BS_BUF_STRIKE];
+        a.rate = (const float *)s.d[BS_BUF_RATE];
+        a.vol = (const float *)s.d[BS_BUF_VOLATILITY];
+        a.otime = (const float *)s.d[BS_BUF_OTIME];
+        a.otype = (const int *)s.d[BS_BUF_OTYPE];
+        a.prices = (float *)s.d[BS_BUF_PRICES];
+        a.refval = (const float *)s.d[BS_BUF_DGREFVAL];
+        pick_f32(c->math, c->unroll, chk)<<<s.blocks, s.threads, 0, s.stream>>>(a, s.count, ec);
+    } else {
+        bsk::StreamsF64 a;
+        a.spt = (const double *)s.d[BS_BUF_SPTPRICE];
+        a.strike = (const double *)s.d[BS_BUF_STRIKE];
+        a.rate = (const double *)s.d[BS_BUF_RATE];
+        a.vol = (const double *)s.d[BS_BUF_VOLATILITY];
+        a.otime = (const double *)s.d[BS_BUF_OTIME];
+        a.otype = (const int *)s.d[BS_BUF_OTYPE];
+        a.prices = (double *)s.d[BS_BUF_PRICES];
+        a.refval = (const double *)s.d[BS_BUF_DGREFVAL];
+        pick_f64(c->unroll, chk)<<<s.blocks, s.threads, 0, s.stream>>>(a, s.count, ec);
+    }
+}
+
+// ---- per-device commands (run on the device's own thread) ------------------------------------------
+void do_setup(bs_gpu_ctx *c, Shard &s)
+{
+    SH_CUDA(cudaSetDevice(s.device));
+    cudaDeviceProp prop;
+    SH_CUDA(cudaGetDeviceProperties(&prop, s.device));
+    s.sm_count = prop.multiProcessorCount;
+    SH_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SH_CUDA(cudaEventCreate(&s.ev0));
+    SH_CUDA(cudaEventCreate(&s.ev1));
+
+    // arena: eight padded streams (DGrefval only when requested)
+    size_t off[BS_BUF_COUNT], total = 0;
+    for (int b = 0; b < BS_BUF_COUNT; b++) {
+        off[b] = total;
+        if (b == BS_BUF_DGREFVAL && !(c->flags & BS_GPU_FLAG_WITH_DGREFVAL)) continue;
+        total += pad256(std::max<size_t>(s.count, 1) * elem_bytes(c, b));
+    }
+    s.arena_bytes = total;
+    SH_CUDA(cudaMalloc((void **)&s.arena, total));
+    for (int b = 0; b < BS_BUF_COUNT; b++) {
+        if (b == BS_BUF_DGREFVAL && !(c->flags & BS_GPU_FLAG_WITH_DGREFVAL)) { s.d[b] = nullptr; continue; }
+        s.d[b] = s.arena + off[b];
+    }
+    SH_CUDA(cudaMalloc((void **)&s.d_err_count, sizeof(unsigned long long)));
+    SH_CUDA(cudaMalloc((void **)&s.d_list_count, sizeof(unsigned int)));
+    SH_CUDA(cudaMalloc((void **)&s.d_list, sizeof(long long) * BS_GPU_MAX_ERROR_LIST));
+    SH_CUDA(cudaMemsetAsync(s.d_err_count, 0, sizeof(unsigned long long), s.stream));
+    SH_CUDA(cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream));
+
+    // launch geometry: persistent grid = SMs x resident CTAs, clipped to the work available
+    const size_t per_group = c->fp_bytes == 4 ? 4 : 2;
+    const size_t groups = std::max<size_t>(s.count / per_group, 1);
+    int threads = c->cfg_threads ? c->cfg_threads : 256;
+    if (!c->cfg_threads && groups < (size_t)s.sm_count * 256) threads = 64;  // tiny inputs: spread over SMs
+    int resident = 0;
+    SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel_ptr(c, false), threads, 0));
+    if (resident < 1) resident = 1;
+    if (c->cfg_blocks_per_sm > 0) resident = c->cfg_blocks_per_sm;
+    size_t blocks = (size_t)s.sm_count * resident;
+    const size_t needed = (groups + threads - 1) / threads;
+    if (blocks > needed) blocks = needed;
+    if (blocks < 1) blocks = 1;
+    s.threads = threads;
+    s.blocks = (int)blocks;
+    SH_CUDA(cudaStreamSynchronize(s.stream));
+}
+
+enum { UP_INPUTS = 1, UP_REFVAL = 2 };
+
+void do_upload(bs_gpu_ctx *c, Shard &s, int what)
+{
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    if (what & UP_INPUTS)
+        for (int b = BS_BUF_SPTPRICE; b <= BS_BUF_OTYPE; b++) {
+            const size_t eb = elem_bytes(c, b);
+            SH_CUDA(cudaMemcpyAsync(s.d[b], (const char *)c->host[b] + s.first * eb, s.count * eb, cudaMemcpyHostToDevice, s.stream));
+        }
+    if ((what & UP_REFVAL) && s.d[BS_BUF_DGREFVAL]) {
+        const size_t eb = elem_bytes(c, BS_BUF_DGREFVAL);
+        SH_CUDA(cudaMemcpyAsync(s.d[BS_BUF_DGREFVAL], (const char *)c->host[BS_BUF_DGREFVAL] + s.first * eb, s.count * eb,
+                                cudaMemcpyHostToDevice, s.stream));
+        s.refval_on_device = true;
+    }
+    SH_CUDA(cudaEventRecord(s.ev1, s.stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.h2d_ms, s.ev0, s.ev1));
+}
+
+void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk)
+{
+    if (chk) {
+        cudaMemsetAsync(s.d_err_count, 0, sizeof(unsigned long long), s.stream);
+        cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream);
+    }
+    // NUM_RUNS real launches (blackscholes.c:318): every run re-reads all inputs and rewrites all prices
+    for (int j = 0; j < num_runs; j++) launch_map(c, s, chk, chk && j == num_runs - 1);
+}
+
+void do_run(bs_gpu_ctx *c, Shard &s)
+{
+    const int num_runs = c->arg_num_runs;
+    const bool chk = c->arg_err_chk != 0;
+    if (s.count == 0) { s.roi_ms = 0; s.err_total = 0; s.list_n = 0; return; }
+    cudaGraphExec_t exec = nullptr;
+    if (!(c->flags & BS_GPU_FLAG_NO_GRAPH)) {
+        GraphKey key = {num_runs, chk ? 1 : 0};
+        auto it = s.graphs.find(key);
+        if (it == s.graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            SH_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_runs(c, s, num_runs, chk);
+            SH_CUDA(cudaStreamEndCapture(s.stream, &graph));
+            SH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+            SH_CUDA(cudaGraphDestroy(graph));
+            SH_CUDA(cudaGraphUpload(exec, s.stream));
+            s.graphs[key] = exec;
+        } else {
+            exec = it->second;
+        }
+    }
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    if (exec) {
+        SH_CUDA(cudaGraphLaunch(exec, s.stream));
+    } else {
+        enqueue_runs(c, s, num_runs, chk);
+        SH_CUDA(cudaGetLastError());
+    }
+    SH_CUDA(cudaEventRecord(s.ev1, s.stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.roi_ms, s.ev0, s.ev1));
+    if (chk) {
+        SH_CUDA(cudaMemcpyAsync(&s.err_total, s.d_err_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        SH_CUDA(cudaMemcpyAsync(&s.list_n, s.d_list_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
+        SH_CUDA(cudaStreamSynchronize(s.stream));
+        const unsigned int keep = std::min<unsigned int>(s.list_n, BS_GPU_MAX_ERROR_LIST);
+        s.list.resize(keep);
+        if (keep) {
+            SH_CUDA(cudaMemcpyAsync(s.list.data(), s.d_list, keep * sizeof(long long), cudaMemcpyDeviceToHost, s.stream));
+            SH_CUDA(cudaStreamSynchronize(s.stream));
+            std::sort(s.list.begin(), s.list.end());
+        }
+    } else {
+        s.err_total = 0;
+        s.list_n = 0;
+        s.list.clear();
+    }
+}
+
+void do_download(bs_gpu_ctx *c, Shard &s)
+{
+    const size_t eb = elem_bytes(c, BS_BUF_PRICES);
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    SH_CUDA(cudaMemcpyAsync((char *)c->host[BS_BUF_PRICES] + s.first * eb, s.d[BS_BUF_PRICES], s.count * eb, cudaMemcpyDeviceToHost, s.stream));
+    SH_CUDA(cudaEventRecord(s.ev1, s.stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.d2h_ms, s.ev0, s.ev1));
+}
+
+// Table values exactly as a reader of the inputgen text would obtain them (text round trip), so that a
+// device-filled set is bit-identical to loading the equivalent file.
+template <typename FP> FP through_text(double v, const char *fmt)
+{
+    char buf[64];
+    snprintf(buf, sizeof(buf), fmt, v);
+    return sizeof(FP) == 4 ? (FP)strtof(buf, nullptr) : (FP)strtod(buf, nullptr);
+}
+
+template <typename FP> void do_fill_typed(bs_gpu_ctx *c, Shard &s)
+{
+    const int R = BS_TABLE_ROWS;
+    const size_t fp_block = pad256(sizeof(FP) * R);
+    const size_t table_bytes = 6 * fp_block + pad256(sizeof(int) * R);
+    if (!s.d_table) {
+        std::vector<char> h(table_bytes, 0);
+        FP *hs = (FP *)(h.data() + 0 * fp_block), *hk = (FP *)(h.data() + 1 * fp_block), *hr = (FP *)(h.data() + 2 * fp_block);
+        FP *hv = (FP *)(h.data() + 3 * fp_block), *ht = (FP *)(h.data() + 4 * fp_block), *hd = (FP *)(h.data() + 5 * fp_block);
+        int *ho = (int *)(h.data() + 6 * fp_block);
+        for (int i = 0; i < R; i++) {
+            const bs_table_row &row = bs_option_table[i];
+            hs[i] = through_text<FP>(row.s, "%.2f");
+            hk[i] = through_text<FP>(row.strike, "%.2f");
+            hr[i] = through_text<FP>(row.r, "%.4f");
+            hv[i] = through_text<FP>(row.v, "%.2f");
+            ht[i] = through_text<FP>(row.t, "%.2f");
+            hd[i] = through_text<FP>(row.dgrefval, "%.18f");
+            ho[i] = (row.option_type == 'P') ? 1 : 0;  // blackscholes.c:761
+        }
+        SH_CUDA(cudaMalloc((void **)&s.d_table, table_bytes));
+        SH_CUDA(cudaMemcpyAsync(s.d_table, h.data(), table_bytes, cudaMemcpyHostToDevice, s.stream));
+        SH_CUDA(cudaStreamSynchronize(s.stream));
+    }
+    bsk::TableDev<FP> tab;
+    tab.spt = (const FP *)(s.d_table + 0 * fp_block);
+    tab.strike = (const FP *)(s.d_table + 1 * fp_block);
+    tab.rate = (const FP *)(s.d_table + 2 * fp_block);
+    tab.vol = (const FP *)(s.d_table + 3 * fp_block);
+    tab.otime = (const FP *)(s.d_table + 4 * fp_block);
+    tab.refval = (const FP *)(s.d_table + 5 * fp_block);
+    tab.otype = (const int *)(s.d_table + 6 * fp_block);
+    tab.rows = R;
+    if (s.count) {
+        const int blocks = (int)std::min<size_t>((s.count + 255) / 256, (size_t)s.sm_count * 8);
+        bsk::bs_fill_synthetic<FP><<<blocks, 256, 0, s.stream>>>(
+            tab, c->arg_first_index + s.first, s.count, (FP *)s.d[BS_BUF_SPTPRICE], (FP *)s.d[BS_BUF_STRIKE],
+            (FP *)s.d[BS_BUF_RATE], (FP *)s.d[BS_BUF_VOLATILITY], (FP *)s.d[BS_BUF_OTIME], (int *)s.d[BS_BUF_OTYPE],
+            (FP *)s.d[BS_BUF_DGREFVAL]);
+        SH_CUDA(cudaGetLastError());
+    }
+    SH_CUDA(cudaStreamSynchronize(s.stream));
+    s.refval_on_device = s.d[BS_BUF_DGREFVAL] != nullptr;
+}
+
+void do_teardown(bs_gpu_ctx *c, Shard &s)
+{
+    (void)c;
+    cudaSetDevice(s.device);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (auto &kv : s.graphs) cudaGraphExecDestroy(kv.second);
+    s.graphs.clear();
+    if (s.d_table) cudaFree(s.d_table);
+    if (s.d_list) cudaFree(s.d_list);
+    if (s.d_list_count) cudaFree(s.d_list_count);
+    if (s.d_err_count) cudaFree(s.d_err_count);
+    if (s.arena) cudaFree(s.arena);
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s.d_table = nullptr; s.d_list = nullptr; s.d_list_count = nullptr; s.d_err_count = nullptr;
+    s.arena = nullptr; s.ev0 = s.ev1 = nullptr; s.stream = nullptr;
+}
+
+void device_thread(bs_gpu_ctx *c, int g)
+{
+    Shard &s = c->shards[g];
+    unsigned long long seen = 0;
+    for (;;) {
+        int cmd;
+        {
+            std::unique_lock<std::mutex> lk(c->mu);
+            c->cv_cmd.wait(lk, [&] { return c->epoch != seen; });
+            seen = c->epoch;
+            cmd = c->cmd;
+        }
+        s.status = BS_GPU_OK;
+        s.err.clear();
+        switch (cmd) {
+        case CMD_SETUP: do_setup(c, s); break;
+        case CMD_UPLOAD: do_upload(c, s, c->arg_upload_what); break;
+        case CMD_RUN: do_run(c, s); break;
+        case CMD_DOWNLOAD: do_download(c, s); break;
+        case CMD_FILL:
+            if (c->fp_bytes == 4) do_fill_typed<float>(c, s); else do_fill_typed<double>(c, s);
+            break;
+        case CMD_TEARDOWN: do_teardown(c, s); break;
+        default: break;
+        }
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            if (--c->pending == 0) c->cv_done.notify_all();
+        }
+        if (cmd == CMD_EXIT) return;
+    }
+}
+
+// Post one command to every device thread and wait for all of them.  Returns the first failure.
+int broadcast(bs_gpu_ctx *c, int cmd)
+{
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        c->cmd = cmd;
+        c->pending = (int)c->shards.size();
+        c->epoch++;
+        c->cv_cmd.notify_all();
+        c->cv_done.wait(lk, [&] { return c->pending == 0; });
+    }
+    for (auto &s : c->shards)
+        if (s.status != BS_GPU_OK) {
+            c->err = s.err;
+            return s.status;
+        }
+    return BS_GPU_OK;
+}
+
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int fail(bs_gpu_ctx *c, int status, const char *msg)
+{
+    if (c) c->err = msg;
+    return status;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C" {
+
+int bs_gpu_abi_version(void) { return BS_GPU_ABI_VERSION; }
+
+const char *bs_gpu_status_string(int status)
+{
+    switch (status) {
+    case BS_GPU_OK: return "ok";
+    case BS_GPU_ERR_INVALID: return "invalid argument";
+    case BS_GPU_ERR_NO_DEVICE: return "no usable CUDA device";
+    case BS_GPU_ERR_CUDA: return "CUDA call failed";
+    case BS_GPU_ERR_NOMEM: return "out of memory";
+    case BS_GPU_ERR_STATE: return "invalid state for this call";
+    default: return "unknown status";
+    }
+}
+
+int bs_gpu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? 0 : BS_GPU_ERR_CUDA;
+    }
+    return n;
+}
+
+int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
+{
+    if (!out) return BS_GPU_ERR_INVALID;
+    *out = nullptr;
+    if (!cfg || cfg->struct_size != sizeof(bs_gpu_config)) return BS_GPU_ERR_INVALID;
+    if (cfg->fp_bytes != 4 && cfg->fp_bytes != 8) return BS_GPU_ERR_INVALID;
+    if (cfg->num_gpus < 1) return BS_GPU_ERR_INVALID;
+    if (cfg->math != BS_MATH_DEFAULT && cfg->math != BS_MATH_IEEE && cfg->math != BS_MATH_FAST) return BS_GPU_ERR_INVALID;
+    if (cfg->unroll != 0 && cfg->unroll != 1 && cfg->unroll != 2 && cfg->unroll != 4) return BS_GPU_ERR_INVALID;
+    if (cfg->threads_per_block != 0 && (cfg->threads_per_block < 32 || cfg->threads_per_block > 256 || cfg->threads_per_block % 32))
+        return BS_GPU_ERR_INVALID;
+    if (cfg->blocks_per_sm < 0 || cfg->blocks_per_sm > 32) return BS_GPU_ERR_INVALID;
+    if (cfg->num_options > 2147483647ull) return BS_GPU_ERR_INVALID;  // the reference's `int numOptions`
+
+    const int have = bs_gpu_device_count();
+    if (have <= 0) return BS_GPU_ERR_NO_DEVICE;  // no CPU fallback, by design
+    if (cfg->num_gpus > have) return BS_GPU_ERR_NO_DEVICE;
+    for (int g = 0; g < cfg->num_gpus; g++) {
+        const int dev = cfg->devices ? cfg->devices[g] : g;
+        if (dev < 0 || dev >= have) return BS_GPU_ERR_NO_DEVICE;
+    }
+
+    bs_gpu_ctx *c = new (std::nothrow) bs_gpu_ctx();
+    if (!c) return BS_GPU_ERR_NOMEM;
+    c->n = cfg->num_options;
+    c->fp_bytes = cfg->fp_bytes;
+    c->flags = cfg->flags;
+    c->math = cfg->math == BS_MATH_DEFAULT ? BS_MATH_FAST : cfg->math;
+    c->cfg_threads = cfg->threads_per_block;
+    c->cfg_blocks_per_sm = cfg->blocks_per_sm;
+    c->unroll = cfg->unroll ? cfg->unroll : 2;
+    c->variant = cfg->variant;
+
+    // contiguous shards; the first N % G shards take one extra option (ff static partitioner rule)
+    const int G = cfg->num_gpus;
+    c->shards.resize(G);
+    const size_t q = c->n / G, r = c->n % G;
+    size_t first = 0;
+    for (int g = 0; g < G; g++) {
+        Shard &s = c->shards[g];
+        s.index = g;
+        s.device = cfg->devices ? cfg->devices[g] : g;
+        s.first = first;
+        s.count = q + ((size_t)g < r ? 1 : 0);
+        first += s.count;
+    }
+
+    // pinned, portable host staging (north_star item 1); the loader writes SoA straight into it
+    if (!(c->flags & BS_GPU_FLAG_NO_HOST_STAGING)) {
+        cudaSetDevice(c->shards[0].device);
+        for (int b = 0; b < BS_BUF_COUNT; b++) {
+            const size_t bytes = std::max<size_t>(c->n, 1) * elem_bytes(c, b);
+            cudaError_t e = cudaHostAlloc(&c->host[b], bytes, cudaHostAllocPortable);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (int k = 0; k < b; k++) cudaFreeHost(c->host[k]);
+                delete c;
+                return BS_GPU_ERR_NOMEM;
+            }
+        }
+    }
+
+    for (int g = 0; g < G; g++) c->shards[g].worker = std::thread(device_thread, c, g);
+    const int st = broadcast(c, CMD_SETUP);
+    if (st != BS_GPU_OK) {
+        fprintf(stderr, "bs_gpu_init: %s\n", c->err.c_str());
+        bs_gpu_fini(c);
+        return st;
+    }
+    *out = c;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_init(bs_gpu_ctx **ctx, int num_gpus, size_t num_options, int fp_bytes)
+{
+    bs_gpu_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.struct_size = sizeof(cfg);
+    cfg.num_options = num_options;
+    cfg.fp_bytes = fp_bytes;
+    cfg.num_gpus = num_gpus;
+    cfg.flags = BS_GPU_FLAG_WITH_DGREFVAL;
+    return bs_gpu_init_ex(ctx, &cfg);
+}
+
+void *bs_gpu_host_buffer(bs_gpu_ctx *c, int which)
+{
+    if (!c || which < 0 || which >= BS_BUF_COUNT) return nullptr;
+    return c->host[which];
+}
+
+int bs_gpu_mark_dirty(bs_gpu_ctx *c)
+{
+    if (!c) return BS_GPU_ERR_INVALID;
+    c->inputs_dirty = true;
+    for (auto &s : c->shards) s.refval_on_device = false;
+    return BS_GPU_OK;
+}
+
+static int upload_impl(bs_gpu_ctx *c, int what)
+{
+    if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "context has no host staging buffers");
+    if ((what & UP_REFVAL) && !(c->flags & BS_GPU_FLAG_WITH_DGREFVAL))
+        return fail(c, BS_GPU_ERR_STATE, "context was created without the DGREFVAL stream");
+    c->arg_upload_what = what;
+    const double t0 = now_ms();
+    const int st = broadcast(c, CMD_UPLOAD);
+    c->timing.wall_ms = now_ms() - t0;
+    if (st != BS_GPU_OK) return st;
+    double mx = 0;
+    for (auto &s : c->shards) mx = std::max<double>(mx, s.h2d_ms);
+    c->timing.h2d_ms = mx;
+    c->timing.h2d_bytes = (unsigned long long)c->n * (((what & UP_INPUTS) ? 5ull * c->fp_bytes + 4ull : 0ull) +
+                                                      ((what & UP_REFVAL) ? (unsigned long long)c->fp_bytes : 0ull));
+    if (what & UP_INPUTS) {
+        c->inputs_dirty = false;
+        c->device_valid = true;
+    }
+    return BS_GPU_OK;
+}
+
+static bool refval_missing(bs_gpu_ctx *c)
+{
+    for (auto &s : c->shards)
+        if (!s.refval_on_device) return true;
+    return false;
+}
+
+/* Copies the six input streams H2D.  DGREFVAL is not an input of the Map: it follows lazily, the first
+ * time a run asks for err_chk. */
+int bs_gpu_upload(bs_gpu_ctx *c)
+{
+    if (!c) return BS_GPU_ERR_INVALID;
+    return upload_impl(c, UP_INPUTS);
+}
+
+int bs_gpu_run(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *num_errors)
+{
+    if (!c || num_runs < 0) return BS_GPU_ERR_INVALID;
+    if (!c->device_valid) return fail(c, BS_GPU_ERR_STATE, "no inputs on the device: call bs_gpu_upload / bs_gpu_fill_synthetic first");
+    if (err_chk) {
+        if (!(c->flags & BS_GPU_FLAG_WITH_DGREFVAL)) return fail(c, BS_GPU_ERR_STATE, "err_chk needs BS_GPU_FLAG_WITH_DGREFVAL");
+        if (refval_missing(c)) {
+            if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "DGREFVAL is not on the device");
+            const int up = upload_impl(c, UP_REFVAL);
+            if (up != BS_GPU_OK) return up;
+        }
+    }
+    c->arg_num_runs = num_runs;
+    c->arg_err_chk = err_chk;
+    const double t0 = now_ms();
+    const int st = broadcast(c, CMD_RUN);
+    c->timing.wall_ms = now_ms() - t0;
+    if (st != BS_GPU_OK) return st;
+    double mx = 0;
+    unsigned long long total = 0, launches = 0;
+    for (auto &s : c->shards) {
+        mx = std::max<double>(mx, s.roi_ms);
+        total += s.err_total;
+        if (s.count) launches += (unsigned long long)num_runs;
+    }
+    c->timing.roi_ms = mx;
+    c->timing.kernel_launches = launches;
+    if (num_errors) *num_errors = total;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_download(bs_gpu_ctx *c)
+{
+    if (!c) return BS_GPU_ERR_INVALID;
+    if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "context has no host staging buffers");
+    const double t0 = now_ms();
+    const int st = broadcast(c, CMD_DOWNLOAD);
+    c->timing.wall_ms = now_ms() - t0;
+    if (st != BS_GPU_OK) return st;
+    double mx = 0;
+    for (auto &s : c->shards) mx = std::max<double>(mx, s.d2h_ms);
+    c->timing.d2h_ms = mx;
+    c->timing.d2h_bytes = (unsigned long long)c->n * c->fp_bytes;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_price(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *num_errors)
+{
+    if (!c || num_runs < 0) return BS_GPU_ERR_INVALID;
+    if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "bs_gpu_price needs host staging; use bs_gpu_run");
+    const double t0 = now_ms();
+    int st;
+    const bool need_refval = err_chk && (c->flags & BS_GPU_FLAG_WITH_DGREFVAL) && refval_missing(c);
+    if (c->inputs_dirty || need_refval) {
+        st = upload_impl(c, (c->inputs_dirty ? UP_INPUTS : 0) | (need_refval ? UP_REFVAL : 0));
+        if (st != BS_GPU_OK) return st;
+    } else {
+        c->timing.h2d_ms = 0;
+        c->timing.h2d_bytes = 0;
+    }
+    st = bs_gpu_run(c, num_runs, err_chk, num_errors);
+    if (st != BS_GPU_OK) return st;
+    st = bs_gpu_download(c);
+    if (st != BS_GPU_OK) return st;
+    c->timing.wall_ms = now_ms() - t0;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_fill_synthetic(bs_gpu_ctx *c, unsigned long long first_index)
+{
+    if (!c) return BS_GPU_ERR_INVALID;
+    c->arg_first_index = first_index;
+    const int st = broadcast(c, CMD_FILL);
+    if (st != BS_GPU_OK) return st;
+    c->device_valid = true;
+    c->inputs_dirty = false;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_read_device(bs_gpu_ctx *c, int which, size_t first, size_t count, void *dst)
+{
+    if (!c || which < 0 || which >= BS_BUF_COUNT || (!dst && count)) return BS_GPU_ERR_INVALID;
+    if (first > c->n || count > c->n - first) return BS_GPU_ERR_INVALID;
+    const size_t eb = elem_bytes(c, which);
+    for (auto &s : c->shards) {
+        const size_t lo = std::max(first, s.first), hi = std::min(first + count, s.first + s.count);
+        if (lo >= hi) continue;
+        if (!s.d[which]) return fail(c, BS_GPU_ERR_STATE, "stream not allocated on the device");
+        cudaError_t e = cudaSetDevice(s.device);
+        if (e == cudaSuccess)
+            e = cudaMemcpy((char *)dst + (lo - first) * eb, (const char *)s.d[which] + (lo - s.first) * eb, (hi - lo) * eb, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            c->err = std::string("bs_gpu_read_device: ") + cudaGetErrorString(e);
+            return BS_GPU_ERR_CUDA;
+        }
+    }
+    return BS_GPU_OK;
+}
+
+long long bs_gpu_errors(bs_gpu_ctx *c, long long *idx, size_t cap)
+{
+    if (!c || (!idx && cap)) return BS_GPU_ERR_INVALID;
+    size_t w = 0;
+    for (auto &s : c->shards)
+        for (long long local : s.list) {
+            if (w >= cap) return (long long)w;
+            idx[w++] = local + (long long)s.first;
+        }
+    return (long long)w;
+}
+
+int bs_gpu_num_shards(bs_gpu_ctx *c) { return c ? (int)c->shards.size() : BS_GPU_ERR_INVALID; }
+
+int bs_gpu_shard(bs_gpu_ctx *c, int g, int *device, size_t *first, size_t *count)
+{
+    if (!c || g < 0 || g >= (int)c->shards.size()) return BS_GPU_ERR_INVALID;
+    if (device) *device = c->shards[g].device;
+    if (first) *first = c->shards[g].first;
+    if (count) *count = c->shards[g].count;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_get_timing(bs_gpu_ctx *c, bs_gpu_timing *out)
+{
+    if (!c || !out) return BS_GPU_ERR_INVALID;
+    *out = c->timing;
+    return BS_GPU_OK;
+}
+
+int bs_gpu_get_launch(bs_gpu_ctx *c, int *math, int *threads_per_block, int *blocks)
+{
+    if (!c || c->shards.empty()) return BS_GPU_ERR_INVALID;
+    if (math) *math = c->math;
+    if (threads_per_block) *threads_per_block = c->shards[0].threads;
+    if (blocks) *blocks = c->shards[0].blocks;
+    return BS_GPU_OK;
+}
+
+const char *bs_gpu_last_error(bs_gpu_ctx *c) { return c ? c->err.c_str() : ""; }
+
+void bs_gpu_fini(bs_gpu_ctx *c)
+{
+    if (!c) return;
+    bool any = false;
+    for (auto &s : c->shards) any = any || s.worker.joinable();
+    if (any) {
+        broadcast(c, CMD_TEARDOWN);
+        broadcast(c, CMD_EXIT);
+        for (auto &s : c->shards)
+            if (s.worker.joinable()) s.worker.join();
+    }
+    for (int b = 0; b < BS_BUF_COUNT; b++)
+        if (c->host[b]) cudaFreeHost(c->host[b]);
+    delete c;
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+/*
+ * bs_io.cpp -- parallel loader / writer behind include/bs_io.h.
+ *
+ * Loader: the file is mmap'ed; all host cores first count whitespace-separated tokens in their byte
+ * range, a prefix sum gives every range its first token number, and then each core converts its tokens
+ * (std::from_chars: correctly rounded, so bit-identical to the strtof/strtod inside fscanf) directly
+ * into the SoA destination arrays: token t belongs to row t/9, field t%9 of the reference's
+ * "%f %f %f %f %f %f %c %f %f" grammar (blackscholes.c:728).  Anything that is not a plain token of the
+ * expected kind (glued fields, '+' signs, hex floats, ...) makes the loader start over with the C
+ * library's fscanf, i.e. the reference's own code path, so odd files behave identically.
+ *
+ * Writer: "%.18f" is produced exactly (the decimal expansion of a binary float is finite, so 18
+ * fractional digits with round-half-even need only a 128-bit integer), validated against snprintf in
+ * tests/test_io.py; non-finite or huge values fall back to snprintf itself.
+ */
+#include "../../include/bs_io.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+struct bs_io_file {
+    std::string path;
+    const char *data = nullptr;  // mmap of the whole file
+    size_t size = 0;
+    size_t body = 0;  // offset just past the header number
+    int fd = -1;
+};
+
+namespace {
+
+inline bool is_space(char ch) { return ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\v' || ch == '\f'; }
+
+int host_threads(int want, size_t work_items, size_t min_per_thread)
+{
+    long n = want > 0 ? want : sysconf(_SC_NPROCESSORS_ONLN);
+    cpu_set_t set;
+    if (want <= 0 && sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n < 1) n = 1;
+    const size_t cap = std::max<size_t>(1, work_items / std::max<size_t>(min_per_thread, 1));
+    return (int)std::min<size_t>((size_t)n, cap);
+}
+
+template <typename F> void parallel_for_chunks(int nthreads, F fn)
+{
+    if (nthreads <= 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nthreads - 1);
+    for (int t = 1; t < nthreads; t++) th.emplace_back(fn, t);
+    fn(0);
+    for (auto &x : th) x.join();
+}
+
+template <typename FP> struct Dest {
+    FP *f[9];  // per field; [6] unused
+    int *otype;
+};
+
+// Convert one token.  Returns false when the token is not a plain decimal float (caller falls back).
+template <typename FP> inline bool parse_fp(const char *b, const char *e, FP *out)
+{
+    FP v;
+    auto r = std::from_chars(b, e, v, std::chars_format::general);
+    if (r.ec != std::errc() || r.ptr != e) return false;
+    // "inf"/"nan" spellings are legal for both parsers but let fscanf decide on anything exotic
+    const char c0 = (*b == '-') ? (e - b > 1 ? b[1] : 0) : *b;
+    if (!((c0 >= '0' && c0 <= '9') || c0 == '.')) return false;
+    *out = v;
+    return true;
+}
+
+template <typename FP>
+int load_fast(const bs_io_file *f, size_t count, const Dest<FP> &dst, int nthreads)
+{
+    const char *buf = f->data;
+    const size_t lo = f->body, hi = f->size;
+    const size_t want_tokens = count * 9;
+    if (count == 0) return BS_IO_OK;
+    const int T = host_threads(nthreads, hi - lo, 1 << 16);
+    std::vector<size_t> start(T + 1), ntok(T + 1, 0);
+    for (int t = 0; t <= T; t++) start[t] = lo + (hi - lo) / T * t;
+    start[T] = hi;
+
+    // pass 1: token starts per byte range
+    parallel_for_chunks(T, [&](int t) {
+        size_t n = 0;
+        bool prev_space = (start[t] == lo) ? true : is_space(buf[start[t] - 1]);
+        for (size_t p = start[t]; p < start[t + 1]; p++) {
+            const bool sp = is_space(buf[p]);
+            n += (!sp && prev_space);
+            prev_space = sp;
+        }
+        ntok[t + 1] = n;
+    });
+    for (int t = 0; t < T; t++) ntok[t + 1] += ntok[t];
+    if (ntok[T] < want_tokens) return BS_IO_ERR_READ;  // short file: let fscanf produce the verdict
+
+    // pass 2: convert
+    std::vector<int> bad(T, 0);
+    parallel_for_chunks(T, [&](int t) {
+        size_t tok = ntok[t];
+        size_t p = start[t];
+        const size_t end = start[t + 1];
+        // skip the tail of a token that started in the previous range
+        if (p > lo && !is_space(buf[p - 1]))
+            while (p < end && !is_space(buf[p])) p++;
+        while (p < end && tok < want_tokens) {
+            while (p < end && is_space(buf[p])) p++;
+            if (p >= end) break;
+            size_t q = p;
+            while (q < hi && !is_space(buf[q])) q++;  // may run into the next range: the token is ours
+            const size_t row = tok / 9;
+            const int field = (int)(tok % 9);
+            if (field == 6) {
+                if (q - p != 1) { bad[t] = 1; return; }
+                dst.otype[row] = (buf[p] == 'P') ? 1 : 0;  // blackscholes.c:761
+            } else {
+                FP v;
+                if (!parse_fp<FP>(buf + p, buf + q, &v)) { bad[t] = 1; return; }
+                if (dst.f[field]) dst.f[field][row] = v;
+            }
+            tok++;
+            p = q;
+        }
+    });
+    for (int t = 0; t < T; t++)
+        if (bad[t]) return BS_IO_ERR_INVALID;
+    return BS_IO_OK;
+}
+
+// The reference's own loop, verbatim in behaviour: used when the fast path met something unusual.
+template <typename FP>
+int load_with_fscanf(const bs_io_file *f, size_t count, const Dest<FP> &dst)
+{
+    FILE *file = fopen(f->path.c_str(), "r");
+    if (!file) return BS_IO_ERR_OPEN;
+    int n = 0;
+    if (fscanf(file, "%i", &n) != 1) { fclose(file); return BS_IO_ERR_READ; }
+    const char *fmt = sizeof(FP) == 4 ? "%f %f %f %f %f %f %c %f %f" : "%lf %lf %lf %lf %lf %lf %c %lf %lf";
+    for (size_t i = 0; i < count; i++) {
+        FP v[8];
+        char ty;
+        const int rv = fscanf(file, fmt, &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &ty, &v[6], &v[7]);
+        if (rv != 9) { fclose(file); return BS_IO_ERR_READ; }
+        for (int k = 0; k < 6; k++)
+            if (dst.f[k]) dst.f[k][i] = v[k];
+        if (dst.f[7]) dst.f[7][i] = v[6];
+        if (dst.f[8]) dst.f[8][i] = v[7];
+        dst.otype[i] = (ty == 'P') ? 1 : 0;
+    }
+    return fclose(file) == 0 ? BS_IO_OK : BS_IO_ERR_CLOSE;
+}
+
+template <typename FP>
+int load_typed(bs_io_file *f, size_t count, void *spt, void *strike, void *rate, void *vol, void *otime, int *otype,
+               void *ref, void *divq, void *divs, int nthreads)
+{
+    Dest<FP> d;
+    d.f[0] = (FP *)spt; d.f[1] = (FP *)strike; d.f[2] = (FP *)rate; d.f[3] = (FP *)divq; d.f[4] = (FP *)vol;
+    d.f[5] = (FP *)otime; d.f[6] = nullptr; d.f[7] = (FP *)divs; d.f[8] = (FP *)ref;
+    d.otype = otype;
+    const int st = load_fast<FP>(f, count, d, nthreads);
+    if (st == BS_IO_OK) return st;
+    return load_with_fscanf<FP>(f, count, d);
+}
+
+// ---- exact "%.18f\n" --------------------------------------------------------------------------
+const uint64_t TEN18 = 1000000000000000000ull;
+
+inline char *put_u64(char *p, uint64_t v)
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// Appends the text printf("%.18f\n", x) would produce; returns the new end.  Needs >= 352 bytes room.
+char *format_price(char *p, double x)
+{
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    const int bexp = (int)((bits >> 52) & 0x7ff);
+    uint64_t mant = bits & 0xfffffffffffffull;
+    if (bexp == 0x7ff || bexp >= 1075 + 10) {  // inf/nan, or |x| >= 2^63: leave it to the C library
+        return p + snprintf(p, 352, "%.18f\n", x);
+    }
+    if (bits >> 63) *p++ = '-';
+    int s;  // x = mant * 2^-s
+    if (bexp == 0) s = 1074; else { mant |= 1ull << 52; s = 1075 - bexp; }
+    uint64_t ipart, frac_num;
+    if (s <= 0) { ipart = mant << (-s); frac_num = 0; s = 1; }
+    else if (s >= 64) { ipart = 0; frac_num = mant; }
+    else { ipart = mant >> s; frac_num = mant & ((1ull << s) - 1); }
+    // q = round_half_even(frac_num * 10^18 / 2^s)
+    uint64_t q = 0;
+    if (frac_num) {
+        const unsigned __int128 P = (unsigned __int128)frac_num * TEN18;  // < 2^113
+        if (s <= 120) {
+            q = (uint64_t)(P >> s);
+            const unsigned __int128 rem = P & ((((unsigned __int128)1) << s) - 1);
+            const unsigned __int128 half = ((unsigned __int128)1) << (s - 1);
+            if (rem > half || (rem == half && (q & 1))) q++;
+        }  // else P < 2^113 <= 2^(s-1)/..: strictly below one half -> 0
+        if (q == TEN18) { q = 0; ipart++; }
+    }
+    p = put_u64(p, ipart);
+    *p++ = '.';
+    char digs[18];
+    for (int i = 17; i >= 0; i--) { digs[i] = (char)('0' + q % 10); q /= 10; }
+    memcpy(p, digs, 18);
+    p += 18;
+    *p++ = '\n';
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
+{
+    if (!path || !file) return BS_IO_ERR_INVALID;
+    *file = nullptr;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return BS_IO_ERR_OPEN;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(fd); return BS_IO_ERR_OPEN; }
+    bs_io_file *f = new (std::nothrow) bs_io_file();
+    if (!f) { close(fd); return BS_IO_ERR_NOMEM; }
+    f->path = path;
+    f->fd = fd;
+    f->size = (size_t)st.st_size;
+    if (f->size) {
+        void *m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); delete f; return BS_IO_ERR_OPEN; }
+        f->data = (const char *)m;
+        madvise(m, f->size, MADV_SEQUENTIAL | MADV_WILLNEED);
+    }
+    // header: fscanf("%i") == optional whitespace, then strtol(base 0)   (blackscholes.c:701)
+    char head[64];
+    size_t p = 0;
+    while (p < f->size && is_space(f->data[p])) p++;
+    const size_t take = std::min<size_t>(sizeof(head) - 1, f->size - p);
+    memcpy(head, f->data ? f->data + p : "", take);
+    head[take] = 0;
+    char *endp = nullptr;
+    const long v = strtol(head, &endp, 0);
+    if (endp == head) { bs_io_close(f); return BS_IO_ERR_READ; }
+    f->body = p + (size_t)(endp - head);
+    if (num_options) *num_options = (long long)(int)v;  // stored into an `int` by the reference
+    *file = f;
+    return BS_IO_OK;
+}
+
+int bs_io_load(bs_io_file *f, int fp_bytes, size_t count, void *spt, void *strike, void *rate, void *vol, void *otime,
+               int *otype, void *dgrefval, void *divq, void *divs, int nthreads)
+{
+    if (!f || (fp_bytes != 4 && fp_bytes != 8)) return BS_IO_ERR_INVALID;
+    if (count && (!spt || !strike || !rate || !vol || !otime || !otype)) return BS_IO_ERR_INVALID;
+    if (fp_bytes == 4) return load_typed<float>(f, count, spt, strike, rate, vol, otime, otype, dgrefval, divq, divs, nthreads);
+    return load_typed<double>(f, count, spt, strike, rate, vol, otime, otype, dgrefval, divq, divs, nthreads);
+}
+
+int bs_io_close(bs_io_file *f)
+{
+    if (!f) return BS_IO_OK;
+    int rc = BS_IO_OK;
+    if (f->data) munmap((void *)f->data, f->size);
+    if (f->fd >= 0 && close(f->fd) != 0) rc = BS_IO_ERR_CLOSE;
+    delete f;
+    return rc;
+}
+
+int bs_io_write_prices(const char *path, int fp_bytes, size_t count, const void *prices, int nthreads)
+{
+    if (!path || (fp_bytes != 4 && fp_bytes != 8) || (count && !prices)) return BS_IO_ERR_INVALID;
+    FILE *file = fopen(path, "w");
+    if (!file) return BS_IO_ERR_OPEN;
+    if (fprintf(file, "%i\n", (int)count) < 0) { fclose(file); return BS_IO_ERR_WRITE; }
+    const size_t BLOCK = 1u << 20;  // rows formatted per round (bounds memory: ~24 MB of text per round)
+    const int T = host_threads(nthreads, std::min(count, BLOCK), 4096);
+    std::vector<std::vector<char>> text(T);
+    std::vector<size_t> used(T);
+    for (size_t base = 0; base < count; base += BLOCK) {
+        const size_t rows = std::min(BLOCK, count - base);
+        parallel_for_chunks(T, [&](int t) {
+            const size_t lo = base + rows * t / T, hi = base + rows * (t + 1) / T;
+            std::vector<char> &out = text[t];
+            if (out.size() < (hi - lo) * 32 + 512) out.resize((hi - lo) * 32 + 512);
+            char *p = out.data();
+            for (size_t i = lo; i < hi; i++) {
+                const double x = fp_bytes == 4 ? (double)((const float *)prices)[i] : ((const double *)prices)[i];
+                if ((size_t)(p - out.data()) + 400 > out.size()) {  // only after a giant snprintf fallback
+                    const size_t off = p - out.data();
+                    out.resize(out.size() * 2);
+                    p = out.data() + off;
+                }
+                p = format_price(p, x);
+            }
+            used[t] = p - out.data();
+        });
+        for (int t = 0; t < T; t++)
+            if (used[t] && fwrite(text[t].data(), 1, used[t], file) != used[t]) { fclose(file); return BS_IO_ERR_WRITE; }
+    }
+    return fclose(file) == 0 ? BS_IO_OK : BS_IO_ERR_CLOSE;
+}
+
+/* Exposed for tests: format one value the way the writer does.  Returns the length (without NUL). */
+int bs_io_format_price(double x, char *out, size_t cap)
+{
+    char tmp[400];
+    char *e = format_price(tmp, x);
+    const size_t n = (size_t)(e - tmp);
+    if (n + 1 > cap) return BS_IO_ERR_INVALID;
+    memcpy(out, tmp, n);
+    out[n] = 0;
+    return (int)n;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Parity of the CUDA Map with the reference (-m gpu; every call goes through the C ABI of libbs_gpu.so).
+
+Three kinds of evidence:
+  1. committed golden outputs of the unmodified reference binaries (tests/golden/*.ref_f32/f64.txt);
+  2. the oracle restatement (bit-identical to the reference, tests/test_oracle.py) on seeded inputs of
+     many sizes, including ragged ones;
+  3. size-independent properties at BASELINE.json's full sizes (10M options): periodicity of the
+     cyclic inputgen set, put-call parity, idempotence over NUM_RUNS, shard-independence.
+Tolerances: fp32 max |delta| <= 1e-4 absolute; fp64 |delta| <= 1e-9*|ref| + 1e-12 (see gpu_util.py).
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from conftest import GOLDEN_CASES, golden_path
+from gpu_util import FP32_ABS_TOL, assert_parity, gpu_prices, inputgen_like, oracle_prices
+from p3arsec_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+MATHS = [(host.MATH_IEEE, "ieee"), (host.MATH_FAST, "fast")]
+
+
+def _golden_inputs(name, fp_bytes):
+    d = host.load_options(golden_path(name, "in.txt"), fp_bytes)
+    return (d["sptprice"], d["strike"], d["rate"], d["volatility"], d["otime"], d["otype"]), d
+
+
+def _golden_prices(name, sfx):
+    n, toks = oracle_lib.read_prices_text(golden_path(name, "ref_%s.txt" % sfx))
+    return np.array([float(t) for t in toks])
+
+
+def test_library_reports_a_device():
+    assert host.device_count() >= 1
+
+
+@pytest.mark.parametrize("math,mname", MATHS)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp32_against_reference_golden(name, math, mname):
+    inputs, d = _golden_inputs(name, 4)
+    got, _, _ = gpu_prices(inputs, 4, num_runs=1, math=math)
+    worst = assert_parity(got, _golden_prices(name, "f32"), 4, "%s/%s" % (name, mname))
+    print("fp32 %-9s %-4s max|delta| = %.3e" % (name, mname, worst))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp64_against_reference_golden(name):
+    inputs, d = _golden_inputs(name, 8)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=1)
+    ref = _golden_prices(name, "f64")
+    worst = assert_parity(got, ref, 8, name)
+    exact = float(np.mean(got == ref))
+    print("fp64 %-9s max|delta| = %.3e, bit-identical on %.1f%% of rows" % (name, worst, 100 * exact))
+
+
+@pytest.mark.parametrize("math,mname", MATHS)
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 37, 255, 256, 257, 1000, 4096, 65537, 1000003])
+def test_fp32_against_oracle_sizes(n, math, mname):
+    inputs = inputgen_like(n, seed=n)
+    got, _, _ = gpu_prices(inputs, 4, num_runs=2, math=math)
+    assert_parity(got, oracle_prices(inputs, 4), 4, "n=%d/%s" % (n, mname))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 37, 257, 4096, 65537, 1000003])
+def test_fp64_against_oracle_sizes(n):
+    inputs = inputgen_like(n, seed=n, dtype=np.float64)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=2)
+    assert_parity(got, oracle_prices(inputs, 8), 8, "n=%d" % n)
+
+
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+def test_empty_input(fp_bytes):
+    with host.BlackScholesGPU(0, fp_bytes=fp_bytes) as bs:
+        assert bs.price(3) == 0
+        assert bs.prices.shape == (0,)
+
+
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+def test_launch_geometry_does_not_change_results(fp_bytes):
+    inputs = inputgen_like(300007, seed=9, dtype=np.float32 if fp_bytes == 4 else np.float64)
+    base, _, _ = gpu_prices(inputs, fp_bytes)
+    for kw in (dict(unroll=1), dict(unroll=4), dict(threads_per_block=128), dict(threads_per_block=64, blocks_per_sm=3),
+               dict(blocks_per_sm=1, unroll=1), dict(use_graph=False)):
+        got, _, _ = gpu_prices(inputs, fp_bytes, **kw)
+        assert got.tobytes() == base.tobytes(), kw
+
+
+def test_num_runs_is_idempotent_and_counts_launches():
+    inputs = inputgen_like(100003, seed=4)
+    with host.BlackScholesGPU(100003) as bs:
+        bs.set_inputs(*inputs)
+        bs.price(1)
+        one = bs.prices.copy()
+        assert bs.timing()["kernel_launches"] == 1
+        bs.prices[:] = -1.0
+        bs.price(host.NUM_RUNS)
+        assert bs.timing()["kernel_launches"] == host.NUM_RUNS
+        assert bs.prices.tobytes() == one.tobytes()
+        assert bs.timing()["h2d_bytes"] == 0            # inputs not dirty: no second upload
+        bs.mark_dirty()
+        bs.price(2)
+        assert bs.timing()["h2d_bytes"] == 100003 * 24  # 5 fp32 + 1 int32 per option
+        assert bs.timing()["d2h_bytes"] == 100003 * 4
+
+
+def test_phases_equal_price():
+    inputs = inputgen_like(50001, seed=6)
+    a, _, _ = gpu_prices(inputs, 4, num_runs=3)
+    with host.BlackScholesGPU(50001) as bs:
+        bs.set_inputs(*inputs)
+        bs.upload()
+        bs.run(3)
+        bs.download()
+        assert bs.prices.tobytes() == a.tobytes()
+        with pytest.raises(host.BsGpuError):
+            host.BlackScholesGPU(10).run(1)  # nothing uploaded yet -> BS_GPU_ERR_STATE
+
+
+# ---- ERR_CHK (blackscholes.c:333-340, :949-951) --------------------------------------------------
+@pytest.mark.parametrize("fp_bytes,sfx", [(4, "f32"), (8, "f64")])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_err_chk_against_reference(name, fp_bytes, sfx):
+    inputs, d = _golden_inputs(name, fp_bytes)
+    runs = 5
+    got, errs, bad = gpu_prices(inputs, fp_bytes, num_runs=runs, dgrefval=d["dgrefval"], err_chk=True)
+    # (a) the checker itself is exact: same verdicts as the oracle's ERR_CHK applied to the GPU's prices
+    cnt, idx = oracle_lib.errchk(got, d["dgrefval"], fp_bytes, cap=65536)
+    assert errs == cnt * runs          # the reference counts once per run
+    assert bad.tolist() == idx.tolist()
+    # (b) and the verdicts are the reference's wherever a row is not within rounding of the 1e-4 threshold
+    gold = json.load(open(golden_path(name, "errchk.json")))[sfx]
+    ref_bad = {int(l.split()[2].rstrip(".")) for l in gold["errors_one_run"]}
+    ref_prices = _golden_prices(name, sfx)
+    margin = np.abs(np.abs(d["dgrefval"].astype(np.float64) - ref_prices) - 1e-4)
+    decided = margin > (3e-5 if fp_bytes == 4 else 1e-9)
+    mine = set(bad.tolist())
+    for i in np.nonzero(decided)[0].tolist():
+        assert (i in mine) == (i in ref_bad), i
+    if name != "edge2k":
+        assert errs == 0 and gold["num_errors_line"] == "Num Errors: 0"
+
+
+def test_err_chk_all_rows_bad_list_is_capped():
+    n = 200000
+    inputs = inputgen_like(n, seed=2)
+    got, errs, bad = gpu_prices(inputs, 4, num_runs=2, dgrefval=np.full(n, -5.0, np.float32), err_chk=True)
+    assert errs == 2 * n
+    assert len(bad) == 65536 and len(set(bad.tolist())) == 65536
+
+
+# ---- full-size properties (BASELINE.json configs[1]/[2]: native = 10M options) -----------------------
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+def test_native_10m_periodicity_and_table_parity(fp_bytes):
+    n = 10_000_000
+    with host.BlackScholesGPU(n, fp_bytes=fp_bytes) as bs:
+        bs.fill_synthetic(0)
+        bs.run(2)
+        bs.download()
+        p = bs.prices
+        # the inputgen set repeats every 1000 rows, so must the prices -- bit for bit, over all 10M
+        assert (p.reshape(-1, 1000) == p[:1000]).all()
+        # and one period equals the reference's answer for the table
+        tab = host.load_options(golden_path("table1k", "in.txt"), fp_bytes)
+        for k in ("sptprice", "strike", "rate", "volatility", "otime", "otype"):
+            assert bs.read_device(k, 0, 1000).tobytes() == tab[k].tobytes(), k
+            assert bs.read_device(k, n - 1000, 1000).tobytes() == tab[k].tobytes(), k
+        assert bs.read_device("dgrefval", 5000, 1000).tobytes() == tab["dgrefval"].tobytes()
+        assert_parity(p[:1000], _golden_prices("table1k", "f32" if fp_bytes == 4 else "f64"), fp_bytes, "table period")
+        # ERR_CHK over the whole set: the reference reports 0 errors on this table
+        assert bs.run(3, err_chk=True) == 0
+
+
+def test_native_10m_put_call_parity_and_bounds():
+    n = 10_000_000
+    s, k, r, v, t, o = inputgen_like(n, seed=77)
+    with host.BlackScholesGPU(n, with_dgrefval=False) as bs:
+        bs.set_inputs(s, k, r, v, t, np.zeros(n, np.int32))
+        bs.price(1)
+        call = bs.prices.astype(np.float64)
+        bs.host("otype")[:] = 1
+        bs.mark_dirty()
+        bs.price(1)
+        put = bs.prices.astype(np.float64)
+    s64, k64, r64, t64 = (a.astype(np.float64) for a in (s, k, r, t))
+    fwd = s64 - k64 * np.exp(-r64 * t64)
+    assert np.abs((call - put) - fwd).max() <= 1e-4        # C - P = S - K e^{-rT}
+    assert (call >= np.maximum(fwd, 0) - 1e-4).all() and (call <= s64 + 1e-4).all()
+    assert (put >= np.maximum(-fwd, 0) - 1e-4).all() and (put <= k64 + 1e-4).all()
+    # spot check 100k random rows against the oracle
+    idx = np.random.RandomState(1).choice(n, 100000, replace=False)
+    ref = oracle_lib.price_map(s[idx], k[idx], r[idx], v[idx], t[idx], np.zeros(len(idx), np.int32), 4)
+    assert np.abs(call[idx] - ref).max() <= FP32_ABS_TOL
+
+
+def test_scaling_homogeneity():
+    # price(2s, 2k) == 2 price(s, k): doubling is exact in binary floating point
+    inputs = list(inputgen_like(100000, seed=12))
+    a, _, _ = gpu_prices(inputs, 4, math=host.MATH_IEEE)
+    inputs[0] = inputs[0] * 2
+    inputs[1] = inputs[1] * 2
+    b, _, _ = gpu_prices(inputs, 4, math=host.MATH_IEEE)
+    assert np.abs(b - 2 * a).max() <= 2e-5
+
+
+# ---- multi-GPU: contiguous shards, no collective -------------------------------------------------------
+def test_sharded_equals_single_device():
+    if host.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 1000003
+    inputs = inputgen_like(n, seed=21)
+    one, _, _ = gpu_prices(inputs, 4, num_runs=2, devices=[0])
+    g = min(host.device_count(), 8)
+    many, _, _ = gpu_prices(inputs, 4, num_runs=2, devices=list(range(g)))
+    assert many.tobytes() == one.tobytes()
+    with host.BlackScholesGPU(n, devices=list(range(g))) as bs:
+        sh = bs.shards()
+        assert [d for d, _, _ in sh] == list(range(g))
+        assert sh[0][1] == 0 and sum(c for _, _, c in sh) == n
+        assert all(sh[i][1] + sh[i][2] == sh[i + 1][1] for i in range(g - 1))
+        assert max(c for _, _, c in sh) - min(c for _, _, c in sh) <= 1
+
+
+# ---- the drop-in driver binary ------------------------------------------------------------------------
+BIN = os.path.join(os.path.dirname(host.LIB_PATH), "..", "bin")
+
+
+@pytest.mark.parametrize("exe,sfx,fp_bytes", [("blackscholes_gpu", "f32", 4), ("blackscholes_gpu_fp64", "f64", 8)])
+@pytest.mark.parametrize("name", ["hull4", "table1k", "ragged37"])
+def test_driver_binary_end_to_end(name, exe, sfx, fp_bytes, tmp_path):
+    out = str(tmp_path / "prices.txt")
+    cp = subprocess.run([os.path.join(BIN, exe), "1", golden_path(name, "in.txt"), out], capture_output=True, text=True)
+    assert cp.returncode == 0, cp.stdout + cp.stderr
+    lines = cp.stdout.splitlines()
+    n = len(_golden_prices(name, sfx))
+    assert lines[0] == "PARSEC Benchmark Suite"
+    assert "Num of Options: %d" % n in lines and "Num of Runs: 100" in lines
+    assert "Size of data: %d" % (n * ((36 if fp_bytes == 4 else 72) + 4)) in lines
+    assert any(l.startswith("roi.time|") for l in lines)
+    cnt, toks = oracle_lib.read_prices_text(out)
+    assert cnt == n and all(len(t.split(".")[1]) == 18 for t in toks)
+    assert_parity(np.array([float(t) for t in toks]), _golden_prices(name, sfx), fp_bytes, name)
+
+
+def test_driver_binary_err_chk_and_usage(tmp_path):
+    out = str(tmp_path / "p.txt")
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu_errchk"), "1", golden_path("table1k", "in.txt"), out],
+                        capture_output=True, text=True)
+    assert cp.returncode == 0 and "Num Errors: 0" in cp.stdout.splitlines()
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu_errchk"), "1", golden_path("edge2k", "in.txt"), out],
+                        capture_output=True, text=True)
+    lines = cp.stdout.splitlines()
+    num = [l for l in lines if l.startswith("Num Errors:")]
+    errs = [l for l in lines if l.startswith("Error on ")]
+    assert len(num) == 1 and int(num[0].split()[-1]) == len(errs) and len(errs) % 100 == 0 and len(errs) > 0
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu")], capture_output=True, text=True)
+    assert cp.returncode == 1 and "Usage:" in cp.stdout and "<nthreads> <inputFile> <outputFile>" in cp.stdout
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", str(tmp_path / "missing.txt"), out], capture_output=True, text=True)
+    assert cp.returncode == 1 and "ERROR: Unable to open file" in cp.stdout
