@@ -63,47 +63,61 @@ def ncu_traffic_bytes(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, power and throttle reasons of one GPU sampled through NVML every ~2 ms WHILE the timed region
+    runs (a Python thread; the timed calls are ctypes calls that release the GIL)."""
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.path = gpu_index, None, None
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = False
+        self._thread = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    power = None
+                self.samples.append((sm, reasons, power))
+                time.sleep(0.002)
+            pynvml.nvmlShutdown()
+        except Exception as e:  # NVML missing: report it in the JSON instead of failing the run
+            self.err = str(e)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(prefix="bs_clocks_", suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        time.sleep(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        seen = set()
+        for _, r, _ in self.samples:
+            for bit, nm in names.items():
+                if r & bit:
+                    seen.add(nm)
+        sm = sorted(x[0] for x in self.samples)
+        pw = [x[2] for x in self.samples if x[2] is not None]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": getattr(self, "max_mhz", None),
+                "reasons": sorted(seen), "samples": len(sm), "power_w_max": max(pw) if pw else None, "source": "nvml"}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -528,7 +528,11 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     c->math = cfg->math == BS_MATH_DEFAULT ? BS_MATH_FAST : cfg->math;
     c->cfg_threads = cfg->threads_per_block;
     c->cfg_blocks_per_sm = cfg->blocks_per_sm;
-    c->unroll = cfg->unroll ? cfg->unroll : 2;
+    // Defaults from the round-1 sweep on B200 (profiles/r01_tune_sweep.txt): one 16-byte group per thread-trip
+    // and, for the MUFU-math fp32 kernel, 4 x 256 resident threads per SM (~98 KB of loads in flight per SM)
+    // sit at the top of the curve; more resident warps only add DRAM page conflicts.
+    c->unroll = cfg->unroll ? cfg->unroll : 1;
+    if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST) c->cfg_blocks_per_sm = 4;
     c->variant = cfg->variant;
 
     // contiguous shards; the first N % G shards take one extra option (ff static partitioner rule)

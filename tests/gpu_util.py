@@ -39,7 +39,16 @@ def oracle_prices(inputs, fp_bytes=4):
     return oracle_lib.price_map(s, k, r, v, t, o, fp_bytes)
 
 
-def assert_parity(got, ref, fp_bytes, what=""):
+def magnitude_scale(spot, strike):
+    """1 inside the inputgen range (spot, strike <= 128); beyond it the fp32 bound grows with the size of
+    the operands, i.e. stays the same number of ulps: a price near 1000 is itself quantised to 6e-5, and
+    the reference's own fp32 build misses its fp64 build by 1.7e-4 on tests/golden/edge2k (3.2e-5 on the
+    in-range table1k)."""
+    mag = np.maximum(np.abs(np.asarray(spot, np.float64)), np.abs(np.asarray(strike, np.float64)))
+    return np.maximum(1.0, mag / 128.0)
+
+
+def assert_parity(got, ref, fp_bytes, what="", scale=None):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     assert got.shape == ref.shape
@@ -47,6 +56,8 @@ def assert_parity(got, ref, fp_bytes, what=""):
     m = np.isfinite(ref)
     d = np.abs(got[m] - ref[m])
     if fp_bytes == 4:
+        if scale is not None:
+            d = d / np.asarray(scale, np.float64)[m]
         worst = float(d.max()) if d.size else 0.0
         assert worst <= FP32_ABS_TOL, "%s fp32 max|delta| = %.3e > 1e-4 at %d" % (what, worst, int(d.argmax()))
         return worst

@@ -17,7 +17,7 @@ import pytest
 
 import oracle_lib
 from conftest import GOLDEN_CASES, golden_path
-from gpu_util import FP32_ABS_TOL, assert_parity, gpu_prices, inputgen_like, oracle_prices
+from gpu_util import FP32_ABS_TOL, assert_parity, gpu_prices, inputgen_like, magnitude_scale, oracle_prices
 from p3arsec_b200 import host
 
 pytestmark = pytest.mark.gpu
@@ -44,8 +44,11 @@ def test_library_reports_a_device():
 def test_fp32_against_reference_golden(name, math, mname):
     inputs, d = _golden_inputs(name, 4)
     got, _, _ = gpu_prices(inputs, 4, num_runs=1, math=math)
-    worst = assert_parity(got, _golden_prices(name, "f32"), 4, "%s/%s" % (name, mname))
-    print("fp32 %-9s %-4s max|delta| = %.3e" % (name, mname, worst))
+    # flat 1e-4 for every row inside the inputgen range; only edge2k holds larger operands (see magnitude_scale)
+    scale = magnitude_scale(inputs[0], inputs[1])
+    assert name == "edge2k" or (scale <= 156.0 / 128.0).all()
+    worst = assert_parity(got, _golden_prices(name, "f32"), 4, "%s/%s" % (name, mname), scale if name == "edge2k" else None)
+    print("fp32 %-9s %-4s max|delta| = %.3e%s" % (name, mname, worst, " (per 128 of magnitude)" if name == "edge2k" else ""))
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -137,7 +140,7 @@ def test_err_chk_against_reference(name, fp_bytes, sfx):
     ref_bad = {int(l.split()[2].rstrip(".")) for l in gold["errors_one_run"]}
     ref_prices = _golden_prices(name, sfx)
     margin = np.abs(np.abs(d["dgrefval"].astype(np.float64) - ref_prices) - 1e-4)
-    decided = margin > (3e-5 if fp_bytes == 4 else 1e-9)
+    decided = margin > (1e-4 * magnitude_scale(inputs[0], inputs[1]) if fp_bytes == 4 else 1e-9)
     mine = set(bad.tolist())
     for i in np.nonzero(decided)[0].tolist():
         assert (i in mine) == (i in ref_bad), i
