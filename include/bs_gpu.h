@@ -99,6 +99,10 @@ typedef struct bs_gpu_timing {
     double roi_ms;   /* last run:   max over devices, CUDA events bracketing the NUM_RUNS launches    */
     double d2h_ms;   /* last download                                                                */
     double wall_ms;  /* host wall clock of the last bs_gpu_price()/upload/run/download call          */
+    double pipeline_ms; /* last bs_gpu_price(): device time from its first copy/launch to its last copy,
+                           max over devices (H2D, launches and D2H overlap, so this is NOT the sum of the
+                           three figures above, which then are: time until the last input chunk landed,
+                           first-to-last kernel, and last kernel to last price chunk)                  */
     unsigned long long kernel_launches; /* pricing kernels launched by the last run, all devices     */
     unsigned long long h2d_bytes;       /* bytes copied by the last upload                           */
     unsigned long long d2h_bytes;       /* bytes copied by the last download                         */
@@ -127,6 +131,9 @@ int bs_gpu_mark_dirty(bs_gpu_ctx *ctx);
 /* The hot path.  H2D of the input streams if they are dirty, then `num_runs` real launches of the
  * pricing kernel per device (every run re-reads all inputs and rewrites all prices; nothing is
  * cached or hoisted across runs), then D2H of the prices into the pinned PRICES buffer.  Blocking.
+ * Copies and launches are pipelined in run order: run 0 is launched chunk by chunk as the input
+ * chunks land, runs 1..num_runs-2 are whole-set launches, and the last run is launched chunk by chunk
+ * with each price chunk copied back as soon as it is complete.
  * With err_chk != 0 every run also evaluates |DGrefval - price| >= 1e-4 (blackscholes.c:335) and
  * *num_errors receives the total over all runs, i.e. the number the reference prints as
  * "Num Errors" (blackscholes.c:950).  num_errors may be NULL. */

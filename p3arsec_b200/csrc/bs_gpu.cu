@@ -37,10 +37,12 @@
 
 namespace {
 
-enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_FILL, CMD_TEARDOWN, CMD_EXIT };
+enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_PRICE, CMD_FILL, CMD_TEARDOWN, CMD_EXIT };
+
+enum { PIPE_CHUNKS = 8 };  // chunks of the first / last run of a pipelined bs_gpu_price()
 
 struct GraphKey {
-    int num_runs, err_chk;
+    int num_runs, err_chk;  // err_chk: 0 = off, 1 = on and the last run records offenders, 2 = on, nothing recorded
     bool operator<(const GraphKey &o) const { return num_runs != o.num_runs ? num_runs < o.num_runs : err_chk < o.err_chk; }
 };
 
@@ -58,8 +60,12 @@ struct Shard {
     long long *d_list = nullptr;
     char *d_table = nullptr;  // synthetic base table, built on first fill
     // execution
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // launches (and the un-pipelined copies)
+    cudaStream_t copy_stream = nullptr;  // H2D / D2H of a pipelined bs_gpu_price()
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;  // timing marks of the pipeline
+    cudaEvent_t ev_in[PIPE_CHUNKS] = {nullptr}, ev_out[PIPE_CHUNKS] = {nullptr};  // chunk landed / chunk priced
+    float pipeline_ms = 0;
     std::map<GraphKey, cudaGraphExec_t> graphs;
     int threads = 0, blocks = 0;
     // results of the last command
@@ -157,38 +163,50 @@ const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
     return c->fp_bytes == 4 ? (const void *)pick_f32(c->math, c->unroll, chk) : (const void *)pick_f64(c->unroll, chk);
 }
 
-void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record)
+// Launch the Map over options [first, first+count) of the shard (first must be a multiple of 4).
+void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t first, size_t count)
 {
+    if (count == 0) return;
     bsk::ErrChk ec;
     ec.count = s.d_err_count;
     ec.list_count = s.d_list_count;
     ec.list = s.d_list;
     ec.list_cap = BS_GPU_MAX_ERROR_LIST;
     ec.record = record;
+    ec.base = (long long)first;
+    // whole-shard launches use the persistent grid chosen at setup; partial ones a proportional share of it
+    int blocks = s.blocks;
+    if (count != s.count) {
+        const size_t per_group = c->fp_bytes == 4 ? 4 : 2;
+        const size_t needed = (count / per_group + s.threads - 1) / s.threads;
+        blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)s.blocks, needed));
+    }
     if (c->fp_bytes == 4) {
         bsk::StreamsF32 a;
-        a.spt = (const float *)s.d[BS_BUF_SPTPRICE];
-        a.strike = (const float *)s.d[BS_BUF_STRIKE];
-        a.rate = (const float *)s.d[BS_BUF_RATE];
-        a.vol = (const float *)s.d[BS_BUF_VOLATILITY];
-        a.otime = (const float *)s.d[BS_BUF_OTIME];
-        a.otype = (const int *)s.d[BS_BUF_OTYPE];
-        a.prices = (float *)s.d[BS_BUF_PRICES];
-        a.refval = (const float *)s.d[BS_BUF_DGREFVAL];
-        pick_f32(c->math, c->unroll, chk)<<<s.blocks, s.threads, 0, s.stream>>>(a, s.count, ec);
+        a.spt = (const float *)s.d[BS_BUF_SPTPRICE] + first;
+        a.strike = (const float *)s.d[BS_BUF_STRIKE] + first;
+        a.rate = (const float *)s.d[BS_BUF_RATE] + first;
+        a.vol = (const float *)s.d[BS_BUF_VOLATILITY] + first;
+        a.otime = (const float *)s.d[BS_BUF_OTIME] + first;
+        a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
+        a.prices = (float *)s.d[BS_BUF_PRICES] + first;
+        a.refval = s.d[BS_BUF_DGREFVAL] ? (const float *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
+        pick_f32(c->math, c->unroll, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
     } else {
         bsk::StreamsF64 a;
-        a.spt = (const double *)s.d[BS_BUF_SPTPRICE];
-        a.strike = (const double *)s.d[BS_BUF_STRIKE];
-        a.rate = (const double *)s.d[BS_BUF_RATE];
-        a.vol = (const double *)s.d[BS_BUF_VOLATILITY];
-        a.otime = (const double *)s.d[BS_BUF_OTIME];
-        a.otype = (const int *)s.d[BS_BUF_OTYPE];
-        a.prices = (double *)s.d[BS_BUF_PRICES];
-        a.refval = (const double *)s.d[BS_BUF_DGREFVAL];
-        pick_f64(c->unroll, chk)<<<s.blocks, s.threads, 0, s.stream>>>(a, s.count, ec);
+        a.spt = (const double *)s.d[BS_BUF_SPTPRICE] + first;
+        a.strike = (const double *)s.d[BS_BUF_STRIKE] + first;
+        a.rate = (const double *)s.d[BS_BUF_RATE] + first;
+        a.vol = (const double *)s.d[BS_BUF_VOLATILITY] + first;
+        a.otime = (const double *)s.d[BS_BUF_OTIME] + first;
+        a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
+        a.prices = (double *)s.d[BS_BUF_PRICES] + first;
+        a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
+        pick_f64(c->unroll, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
     }
 }
+
+void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record) { launch_map_range(c, s, chk, record, 0, s.count); }
 
 // ---- per-device commands (run on the device's own thread) ------------------------------------------
 void do_setup(bs_gpu_ctx *c, Shard &s)
@@ -198,8 +216,16 @@ void do_setup(bs_gpu_ctx *c, Shard &s)
     SH_CUDA(cudaGetDeviceProperties(&prop, s.device));
     s.sm_count = prop.multiProcessorCount;
     SH_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SH_CUDA(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
     SH_CUDA(cudaEventCreate(&s.ev0));
     SH_CUDA(cudaEventCreate(&s.ev1));
+    SH_CUDA(cudaEventCreate(&s.ev_h2d));
+    SH_CUDA(cudaEventCreate(&s.ev_k0));
+    SH_CUDA(cudaEventCreate(&s.ev_k1));
+    for (int i = 0; i < PIPE_CHUNKS; i++) {
+        SH_CUDA(cudaEventCreateWithFlags(&s.ev_in[i], cudaEventDisableTiming));
+        SH_CUDA(cudaEventCreateWithFlags(&s.ev_out[i], cudaEventDisableTiming));
+    }
 
     // arena: eight padded streams (DGrefval only when requested)
     size_t off[BS_BUF_COUNT], total = 0;
@@ -259,48 +285,62 @@ void do_upload(bs_gpu_ctx *c, Shard &s, int what)
     SH_CUDA(cudaEventElapsedTime(&s.h2d_ms, s.ev0, s.ev1));
 }
 
-void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk)
+// NUM_RUNS real launches (blackscholes.c:318): every run re-reads all inputs and rewrites all prices
+void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last)
 {
-    if (chk) {
-        cudaMemsetAsync(s.d_err_count, 0, sizeof(unsigned long long), s.stream);
-        cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream);
-    }
-    // NUM_RUNS real launches (blackscholes.c:318): every run re-reads all inputs and rewrites all prices
-    for (int j = 0; j < num_runs; j++) launch_map(c, s, chk, chk && j == num_runs - 1);
+    for (int j = 0; j < num_runs; j++) launch_map(c, s, chk, chk && record_last && j == num_runs - 1);
 }
+
+void reset_err_counters(Shard &s)
+{
+    cudaMemsetAsync(s.d_err_count, 0, sizeof(unsigned long long), s.stream);
+    cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream);
+}
+
+// `num_runs` whole-shard launches as one cached CUDA graph (or nullptr when graphs are disabled)
+cudaGraphExec_t runs_graph(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last)
+{
+    if ((c->flags & BS_GPU_FLAG_NO_GRAPH) || num_runs <= 0) return nullptr;
+    GraphKey key = {num_runs, chk ? (record_last ? 1 : 2) : 0};
+    auto it = s.graphs.find(key);
+    if (it != s.graphs.end()) return it->second;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return nullptr;
+    enqueue_runs(c, s, num_runs, chk, record_last);
+    if (cudaStreamEndCapture(s.stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return nullptr; }
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return nullptr; }
+    cudaGraphDestroy(graph);
+    cudaGraphUpload(exec, s.stream);
+    s.graphs[key] = exec;
+    return exec;
+}
+
+void fetch_err_results(bs_gpu_ctx *c, Shard &s, bool chk);
 
 void do_run(bs_gpu_ctx *c, Shard &s)
 {
     const int num_runs = c->arg_num_runs;
     const bool chk = c->arg_err_chk != 0;
-    if (s.count == 0) { s.roi_ms = 0; s.err_total = 0; s.list_n = 0; return; }
-    cudaGraphExec_t exec = nullptr;
-    if (!(c->flags & BS_GPU_FLAG_NO_GRAPH)) {
-        GraphKey key = {num_runs, chk ? 1 : 0};
-        auto it = s.graphs.find(key);
-        if (it == s.graphs.end()) {
-            cudaGraph_t graph = nullptr;
-            SH_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-            enqueue_runs(c, s, num_runs, chk);
-            SH_CUDA(cudaStreamEndCapture(s.stream, &graph));
-            SH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-            SH_CUDA(cudaGraphDestroy(graph));
-            SH_CUDA(cudaGraphUpload(exec, s.stream));
-            s.graphs[key] = exec;
-        } else {
-            exec = it->second;
-        }
-    }
+    if (s.count == 0) { s.roi_ms = 0; s.err_total = 0; s.list_n = 0; s.list.clear(); return; }
+    cudaGraphExec_t exec = runs_graph(c, s, num_runs, chk, true);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    if (chk) reset_err_counters(s);
     if (exec) {
         SH_CUDA(cudaGraphLaunch(exec, s.stream));
     } else {
-        enqueue_runs(c, s, num_runs, chk);
+        enqueue_runs(c, s, num_runs, chk, true);
         SH_CUDA(cudaGetLastError());
     }
     SH_CUDA(cudaEventRecord(s.ev1, s.stream));
     SH_CUDA(cudaEventSynchronize(s.ev1));
     SH_CUDA(cudaEventElapsedTime(&s.roi_ms, s.ev0, s.ev1));
+    fetch_err_results(c, s, chk);
+}
+
+void fetch_err_results(bs_gpu_ctx *c, Shard &s, bool chk)
+{
+    (void)c;
     if (chk) {
         SH_CUDA(cudaMemcpyAsync(&s.err_total, s.d_err_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
         SH_CUDA(cudaMemcpyAsync(&s.list_n, s.d_list_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
@@ -317,6 +357,106 @@ void do_run(bs_gpu_ctx *c, Shard &s)
         s.list_n = 0;
         s.list.clear();
     }
+}
+
+// bs_gpu_price() on one device: copies and launches pipelined IN RUN ORDER.
+//   copy stream   : H2D chunk 0..7 ........................................ D2H chunk 0..7 (as each is priced)
+//   launch stream : run 0 chunk 0..7 (each after its inputs landed) | runs 1..R-2 whole-shard | run R-1 chunk 0..7
+// Every run still reads every input from HBM and writes every price; only the first and the last run are
+// cut into PIPE_CHUNKS launches so that PCIe traffic hides behind them.
+void do_price(bs_gpu_ctx *c, Shard &s)
+{
+    const int R = c->arg_num_runs;
+    const bool chk = c->arg_err_chk != 0;
+    const int what = c->arg_upload_what;
+    s.h2d_ms = s.roi_ms = s.d2h_ms = s.pipeline_ms = 0;
+    if (s.count == 0) { s.err_total = 0; s.list_n = 0; s.list.clear(); return; }
+
+    // chunk boundaries: multiples of 1024 options keep every stream 16-byte aligned
+    size_t lo[PIPE_CHUNKS + 1];
+    const size_t per = ((s.count + PIPE_CHUNKS - 1) / PIPE_CHUNKS + 1023) & ~(size_t)1023;
+    for (int k = 0; k <= PIPE_CHUNKS; k++) lo[k] = std::min(s.count, per * (size_t)k);
+    const size_t pe = elem_bytes(c, BS_BUF_PRICES);
+
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev0, 0));
+    if (chk) reset_err_counters(s);
+
+    // ---- inputs: chunked H2D on the copy stream
+    if (what) {
+        for (int k = 0; k < PIPE_CHUNKS; k++) {
+            const size_t n = lo[k + 1] - lo[k];
+            if (n) {
+                if (what & UP_INPUTS)
+                    for (int b = BS_BUF_SPTPRICE; b <= BS_BUF_OTYPE; b++) {
+                        const size_t eb = elem_bytes(c, b);
+                        SH_CUDA(cudaMemcpyAsync((char *)s.d[b] + lo[k] * eb, (const char *)c->host[b] + (s.first + lo[k]) * eb, n * eb,
+                                                cudaMemcpyHostToDevice, s.copy_stream));
+                    }
+                if ((what & UP_REFVAL) && s.d[BS_BUF_DGREFVAL]) {
+                    const size_t eb = elem_bytes(c, BS_BUF_DGREFVAL);
+                    SH_CUDA(cudaMemcpyAsync((char *)s.d[BS_BUF_DGREFVAL] + lo[k] * eb, (const char *)c->host[BS_BUF_DGREFVAL] + (s.first + lo[k]) * eb,
+                                            n * eb, cudaMemcpyHostToDevice, s.copy_stream));
+                }
+            }
+            SH_CUDA(cudaEventRecord(s.ev_in[k], s.copy_stream));
+        }
+        if ((what & UP_REFVAL) && s.d[BS_BUF_DGREFVAL]) s.refval_on_device = true;
+    }
+    SH_CUDA(cudaEventRecord(s.ev_h2d, s.copy_stream));
+
+    // ---- runs
+    int done = 0;
+    bool k0_marked = false;
+    auto mark_k0 = [&]() { if (!k0_marked) { cudaEventRecord(s.ev_k0, s.stream); k0_marked = true; } };
+    if (R >= 1 && what) {  // run 0 follows the input chunks (it is also the last run when R == 1)
+        const bool last = (R == 1);
+        for (int k = 0; k < PIPE_CHUNKS; k++) {
+            SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_in[k], 0));
+            mark_k0();
+            launch_map_range(c, s, chk, chk && last, lo[k], lo[k + 1] - lo[k]);
+            if (last) SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
+        }
+        done = 1;
+    } else if (what) {
+        SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_h2d, 0));  // R == 0: nothing to overlap with
+    }
+    mark_k0();
+    const int middle = std::max(0, R - done - 1);  // whole-shard runs between the pipelined first and last
+    if (middle > 0) {
+        cudaGraphExec_t exec = runs_graph(c, s, middle, chk, false);
+        if (exec) SH_CUDA(cudaGraphLaunch(exec, s.stream));
+        else enqueue_runs(c, s, middle, chk, false);
+        done += middle;
+    }
+    bool out_marked = (R == 1 && what);
+    if (done < R) {  // the last run, chunk by chunk, each chunk's prices leaving as soon as they exist
+        for (int k = 0; k < PIPE_CHUNKS; k++) {
+            launch_map_range(c, s, chk, chk, lo[k], lo[k + 1] - lo[k]);
+            SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
+        }
+        out_marked = true;
+    }
+    SH_CUDA(cudaGetLastError());
+    SH_CUDA(cudaEventRecord(s.ev_k1, s.stream));
+
+    // ---- prices: chunked D2H on the copy stream
+    for (int k = 0; k < PIPE_CHUNKS; k++) {
+        const size_t n = lo[k + 1] - lo[k];
+        if (out_marked) SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_out[k], 0));
+        else if (k == 0) SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_k1, 0));
+        if (n)
+            SH_CUDA(cudaMemcpyAsync((char *)c->host[BS_BUF_PRICES] + (s.first + lo[k]) * pe, (const char *)s.d[BS_BUF_PRICES] + lo[k] * pe, n * pe,
+                                    cudaMemcpyDeviceToHost, s.copy_stream));
+    }
+    SH_CUDA(cudaEventRecord(s.ev1, s.copy_stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaStreamSynchronize(s.stream));
+    SH_CUDA(cudaEventElapsedTime(&s.pipeline_ms, s.ev0, s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.h2d_ms, s.ev0, s.ev_h2d));
+    SH_CUDA(cudaEventElapsedTime(&s.roi_ms, s.ev_k0, s.ev_k1));
+    SH_CUDA(cudaEventElapsedTime(&s.d2h_ms, s.ev_k1, s.ev1));
+    fetch_err_results(c, s, chk);
 }
 
 void do_download(bs_gpu_ctx *c, Shard &s)
@@ -395,9 +535,15 @@ void do_teardown(bs_gpu_ctx *c, Shard &s)
     if (s.d_list_count) cudaFree(s.d_list_count);
     if (s.d_err_count) cudaFree(s.d_err_count);
     if (s.arena) cudaFree(s.arena);
-    if (s.ev0) cudaEventDestroy(s.ev0);
-    if (s.ev1) cudaEventDestroy(s.ev1);
+    for (cudaEvent_t e : {s.ev0, s.ev1, s.ev_h2d, s.ev_k0, s.ev_k1})
+        if (e) cudaEventDestroy(e);
+    for (int i = 0; i < PIPE_CHUNKS; i++) {
+        if (s.ev_in[i]) cudaEventDestroy(s.ev_in[i]);
+        if (s.ev_out[i]) cudaEventDestroy(s.ev_out[i]);
+    }
+    if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     if (s.stream) cudaStreamDestroy(s.stream);
+    s.copy_stream = nullptr;
     s.d_table = nullptr; s.d_list = nullptr; s.d_list_count = nullptr; s.d_err_count = nullptr;
     s.arena = nullptr; s.ev0 = s.ev1 = nullptr; s.stream = nullptr;
 }
@@ -421,6 +567,7 @@ void device_thread(bs_gpu_ctx *c, int g)
         case CMD_UPLOAD: do_upload(c, s, c->arg_upload_what); break;
         case CMD_RUN: do_run(c, s); break;
         case CMD_DOWNLOAD: do_download(c, s); break;
+        case CMD_PRICE: do_price(c, s); break;
         case CMD_FILL:
             if (c->fp_bytes == 4) do_fill_typed<float>(c, s); else do_fill_typed<double>(c, s);
             break;
@@ -688,21 +835,37 @@ int bs_gpu_price(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *n
 {
     if (!c || num_runs < 0) return BS_GPU_ERR_INVALID;
     if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "bs_gpu_price needs host staging; use bs_gpu_run");
+    if (err_chk && !(c->flags & BS_GPU_FLAG_WITH_DGREFVAL)) return fail(c, BS_GPU_ERR_STATE, "err_chk needs BS_GPU_FLAG_WITH_DGREFVAL");
+    const bool need_refval = err_chk && refval_missing(c);
+    const int what = (c->inputs_dirty ? UP_INPUTS : 0) | (need_refval ? UP_REFVAL : 0);
+    if (!c->inputs_dirty && !c->device_valid) return fail(c, BS_GPU_ERR_STATE, "no inputs on the device");
+    c->arg_num_runs = num_runs;
+    c->arg_err_chk = err_chk;
+    c->arg_upload_what = what;
     const double t0 = now_ms();
-    int st;
-    const bool need_refval = err_chk && (c->flags & BS_GPU_FLAG_WITH_DGREFVAL) && refval_missing(c);
-    if (c->inputs_dirty || need_refval) {
-        st = upload_impl(c, (c->inputs_dirty ? UP_INPUTS : 0) | (need_refval ? UP_REFVAL : 0));
-        if (st != BS_GPU_OK) return st;
-    } else {
-        c->timing.h2d_ms = 0;
-        c->timing.h2d_bytes = 0;
-    }
-    st = bs_gpu_run(c, num_runs, err_chk, num_errors);
-    if (st != BS_GPU_OK) return st;
-    st = bs_gpu_download(c);
-    if (st != BS_GPU_OK) return st;
+    const int st = broadcast(c, CMD_PRICE);
     c->timing.wall_ms = now_ms() - t0;
+    if (st != BS_GPU_OK) return st;
+    unsigned long long total = 0, launches = 0;
+    c->timing.h2d_ms = c->timing.roi_ms = c->timing.d2h_ms = c->timing.pipeline_ms = 0;
+    for (auto &s : c->shards) {
+        c->timing.h2d_ms = std::max<double>(c->timing.h2d_ms, s.h2d_ms);
+        c->timing.roi_ms = std::max<double>(c->timing.roi_ms, s.roi_ms);
+        c->timing.d2h_ms = std::max<double>(c->timing.d2h_ms, s.d2h_ms);
+        c->timing.pipeline_ms = std::max<double>(c->timing.pipeline_ms, s.pipeline_ms);
+        total += s.err_total;
+        if (s.count) launches += (unsigned long long)num_runs;
+    }
+    // "launches" counts runs (one logical launch of the Map per run and device), not the chunk launches
+    c->timing.kernel_launches = launches;
+    c->timing.h2d_bytes = (unsigned long long)c->n * (((what & UP_INPUTS) ? 5ull * c->fp_bytes + 4ull : 0ull) +
+                                                      ((what & UP_REFVAL) ? (unsigned long long)c->fp_bytes : 0ull));
+    c->timing.d2h_bytes = (unsigned long long)c->n * c->fp_bytes;
+    if (what & UP_INPUTS) {
+        c->inputs_dirty = false;
+        c->device_valid = true;
+    }
+    if (num_errors) *num_errors = total;
     return BS_GPU_OK;
 }
 

@@ -222,6 +222,7 @@ struct ErrChk {
     long long *list;            // their shard-local indices
     unsigned int list_cap;
     int record;                 // 1 on the run whose offenders are listed
+    long long base;             // shard-local index of element 0 of this launch (chunked launches)
 };
 
 __device__ __forceinline__ bool err_bad(float price, float ref) { return (double)fabsf(ref - price) >= 1e-4; }
@@ -231,7 +232,7 @@ __device__ __forceinline__ void err_note(const ErrChk &ec, size_t idx)
 {
     if (ec.record) {
         unsigned int slot = atomicAdd(ec.list_count, 1u);
-        if (slot < ec.list_cap) ec.list[slot] = (long long)idx;
+        if (slot < ec.list_cap) ec.list[slot] = ec.base + (long long)idx;
     }
 }
 

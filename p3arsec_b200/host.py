@@ -58,6 +58,7 @@ class Timing(ctypes.Structure):
         ("roi_ms", ctypes.c_double),
         ("d2h_ms", ctypes.c_double),
         ("wall_ms", ctypes.c_double),
+        ("pipeline_ms", ctypes.c_double),
         ("kernel_launches", ctypes.c_ulonglong),
         ("h2d_bytes", ctypes.c_ulonglong),
         ("d2h_bytes", ctypes.c_ulonglong),

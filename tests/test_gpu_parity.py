@@ -111,6 +111,34 @@ def test_num_runs_is_idempotent_and_counts_launches():
         assert bs.timing()["d2h_bytes"] == 100003 * 4
 
 
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+def test_pipelined_price_any_run_count(fp_bytes):
+    # bs_gpu_price pipelines run 0 with the H2D chunks and the last run with the D2H chunks: every run
+    # count (0 = copy only, 1 = first is last, 2 = no whole-shard run in between, ...) gives the same prices
+    dt = np.float32 if fp_bytes == 4 else np.float64
+    n = 300007
+    inputs = inputgen_like(n, seed=31, dtype=dt)
+    ref = oracle_prices(inputs, fp_bytes)
+    with host.BlackScholesGPU(n, fp_bytes=fp_bytes) as bs:
+        bs.set_inputs(*inputs)
+        bs.price(0)                                   # uploads, launches nothing
+        assert bs.timing()["kernel_launches"] == 0
+        first = None
+        for runs in (1, 2, 3, 7):
+            for dirty in (True, False):
+                bs.prices[:] = -7.0
+                if dirty:
+                    bs.mark_dirty()
+                bs.price(runs)
+                tm = bs.timing()
+                assert tm["h2d_bytes"] == (n * (5 * fp_bytes + 4) if dirty else 0) and tm["d2h_bytes"] == n * fp_bytes
+                assert tm["pipeline_ms"] > 0 and tm["kernel_launches"] == runs
+                assert_parity(bs.prices, ref, fp_bytes, "runs=%d" % runs)
+                if first is None:
+                    first = bs.prices.copy()
+                assert bs.prices.tobytes() == first.tobytes()
+
+
 def test_phases_equal_price():
     inputs = inputgen_like(50001, seed=6)
     a, _, _ = gpu_prices(inputs, 4, num_runs=3)
@@ -264,3 +292,26 @@ def test_driver_binary_err_chk_and_usage(tmp_path):
     assert cp.returncode == 1 and "Usage:" in cp.stdout and "<nthreads> <inputFile> <outputFile>" in cp.stdout
     cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", str(tmp_path / "missing.txt"), out], capture_output=True, text=True)
     assert cp.returncode == 1 and "ERROR: Unable to open file" in cp.stdout
+
+
+# ---- the reference's OWN driver with only its Map swapped (integration/blackscholes.c.enable_cuda.patch) ----
+@pytest.mark.skipif(oracle_lib.ref_binary("bs_ref_cuda") is None, reason="oracle/_ref/bs_ref_cuda not built")
+@pytest.mark.parametrize("exe,sfx,fp_bytes", [("bs_ref_cuda", "f32", 4), ("bs_ref_cuda_fp64", "f64", 8)])
+@pytest.mark.parametrize("name", ["hull4", "table1k", "ragged37"])
+def test_reference_driver_with_cuda_map(name, exe, sfx, fp_bytes, tmp_path):
+    out = str(tmp_path / "prices.txt")
+    stdout, roi = oracle_lib.run_ref(exe, 1, golden_path(name, "in.txt"), out)
+    assert roi is not None and "Num of Runs: 100" in stdout
+    cnt, toks = oracle_lib.read_prices_text(out)
+    assert_parity(np.array([float(t) for t in toks]), _golden_prices(name, sfx), fp_bytes, name)
+
+
+@pytest.mark.skipif(oracle_lib.ref_binary("bs_ref_cuda_errchk") is None, reason="oracle/_ref/bs_ref_cuda_errchk not built")
+def test_reference_driver_with_cuda_map_err_chk(tmp_path):
+    stdout, _ = oracle_lib.run_ref("bs_ref_cuda_errchk", 1, golden_path("table1k", "in.txt"), str(tmp_path / "p.txt"))
+    assert "Num Errors: 0" in stdout.splitlines()
+    stdout, _ = oracle_lib.run_ref("bs_ref_cuda_errchk", 1, golden_path("edge2k", "in.txt"), str(tmp_path / "p.txt"))
+    lines = stdout.splitlines()
+    errs = [l for l in lines if l.startswith("Error on ")]
+    num = int([l for l in lines if l.startswith("Num Errors:")][0].split()[-1])
+    assert num == len(errs) and num % 100 == 0 and num >= 4800
