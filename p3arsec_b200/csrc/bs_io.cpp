@@ -42,7 +42,8 @@ struct bs_io_file {
 
 namespace {
 
-inline bool is_space(char ch) { return ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\v' || ch == '\f'; }
+// isspace() of the C locale: ' ' and \t \n \v \f \r (9..13)
+inline bool is_space(char ch) { return ch == ' ' || (unsigned char)(ch - 9) <= 4; }
 
 int host_threads(int want, size_t work_items, size_t min_per_thread)
 {
@@ -69,16 +70,75 @@ template <typename FP> struct Dest {
     int *otype;
 };
 
+const double POW10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18,
+                          1e19, 1e20, 1e21, 1e22};
+
 // Convert one token.  Returns false when the token is not a plain decimal float (caller falls back).
+// Fast path (Clinger): a plain decimal [-]ddd[.ddd] whose digit string is an integer m exactly representable
+// in FP (m < 2^24 for float, < 2^53 for double) divided by an exactly representable power of ten is ONE
+// correctly rounded division, hence equal to strtof/strtod.  Plain decimals that are not wanted (`out` NULL,
+// e.g. the 20-digit DGrefval column of a build without ERR_CHK) are validated syntactically and skipped: such
+// a string cannot fail to convert.  Everything else goes through std::from_chars.
 template <typename FP> inline bool parse_fp(const char *b, const char *e, FP *out)
 {
+    {
+        const char *p = b;
+        const bool neg = (p < e && *p == '-');
+        if (neg) p++;
+        uint64_t m = 0;
+        int digits = 0, frac = 0, int_digits = 0;
+        bool seen_dot = false, plain = (p < e);
+        for (; p < e; p++) {
+            const unsigned d = (unsigned)(*p - '0');
+            if (d <= 9) {
+                if (digits < 19) m = m * 10 + d;
+                digits++;
+                if (seen_dot) frac++; else int_digits++;
+            } else if (*p == '.' && !seen_dot) {
+                seen_dot = true;
+            } else {
+                plain = false;
+                break;
+            }
+        }
+        if (plain && digits > 0 && int_digits <= 30) {
+            if (!out) return true;
+            const uint64_t exact_limit = sizeof(FP) == 4 ? (1ull << 24) : (1ull << 53);
+            const int pow_limit = sizeof(FP) == 4 ? 10 : 22;
+            if (digits <= 19 && m < exact_limit && frac <= pow_limit) {
+                const FP v = (FP)m / (FP)POW10[frac];
+                *out = neg ? -v : v;
+                return true;
+            }
+        }
+    }
     FP v;
+    if (sizeof(FP) == 4) {
+        // libstdc++'s from_chars<float> serialises under load (measured 7x slower per token with 8 threads);
+        // from_chars<double> does not.  Rounding the correctly rounded double to float is itself correctly rounded
+        // unless that double IS a float midpoint (low 29 mantissa bits == 1000...0): rounding to double is
+        // monotone and midpoints are doubles, so otherwise text and double lie on the same side of every
+        // midpoint.  Midpoints and values outside the normal float range take the float parser.
+        double d;
+        auto rd = std::from_chars(b, e, d, std::chars_format::general);
+        if (rd.ec == std::errc() && rd.ptr == e) {
+            uint64_t bits;
+            memcpy(&bits, &d, 8);
+            const double ad = d < 0 ? -d : d;
+            if ((bits & 0x1fffffffull) != 0x10000000ull && (ad == 0.0 || (ad > 1e-30 && ad < 1e30))) {
+                const char c0 = (*b == '-') ? (e - b > 1 ? b[1] : 0) : *b;
+                if (!((c0 >= '0' && c0 <= '9') || c0 == '.')) return false;
+                if (out) *out = (FP)d;
+                return true;
+            }
+        }
+    }
     auto r = std::from_chars(b, e, v, std::chars_format::general);
     if (r.ec != std::errc() || r.ptr != e) return false;
     // "inf"/"nan" spellings are legal for both parsers but let fscanf decide on anything exotic
     const char c0 = (*b == '-') ? (e - b > 1 ? b[1] : 0) : *b;
     if (!((c0 >= '0' && c0 <= '9') || c0 == '.')) return false;
-    *out = v;
+    if (out) *out = v;
     return true;
 }
 
@@ -96,13 +156,11 @@ int load_fast(const bs_io_file *f, size_t count, const Dest<FP> &dst, int nthrea
 
     // pass 1: token starts per byte range
     parallel_for_chunks(T, [&](int t) {
-        size_t n = 0;
-        bool prev_space = (start[t] == lo) ? true : is_space(buf[start[t] - 1]);
-        for (size_t p = start[t]; p < start[t + 1]; p++) {
-            const bool sp = is_space(buf[p]);
-            n += (!sp && prev_space);
-            prev_space = sp;
-        }
+        // a token starts where a non-space follows a space; written without a loop-carried flag so that the
+        // compiler vectorises it
+        size_t n = 0, p = start[t];
+        if (p == lo && p < start[t + 1]) { n += !is_space(buf[p]); p++; }
+        for (; p < start[t + 1]; p++) n += (size_t)(!is_space(buf[p]) & is_space(buf[p - 1]));
         ntok[t + 1] = n;
     });
     for (int t = 0; t < T; t++) ntok[t + 1] += ntok[t];
@@ -128,9 +186,8 @@ int load_fast(const bs_io_file *f, size_t count, const Dest<FP> &dst, int nthrea
                 if (q - p != 1) { bad[t] = 1; return; }
                 dst.otype[row] = (buf[p] == 'P') ? 1 : 0;  // blackscholes.c:761
             } else {
-                FP v;
-                if (!parse_fp<FP>(buf + p, buf + q, &v)) { bad[t] = 1; return; }
-                if (dst.f[field]) dst.f[field][row] = v;
+                FP *slot = dst.f[field] ? dst.f[field] + row : nullptr;
+                if (!parse_fp<FP>(buf + p, buf + q, slot)) { bad[t] = 1; return; }
             }
             tok++;
             p = q;
@@ -246,7 +303,7 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
     f->fd = fd;
     f->size = (size_t)st.st_size;
     if (f->size) {
-        void *m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE, fd, 0);
+        void *m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
         if (m == MAP_FAILED) { close(fd); delete f; return BS_IO_ERR_OPEN; }
         f->data = (const char *)m;
         madvise(m, f->size, MADV_SEQUENTIAL | MADV_WILLNEED);
