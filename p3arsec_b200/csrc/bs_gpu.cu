@@ -150,17 +150,23 @@ KernelF32 pick_f32(int math, int unroll, bool chk)
     if (math == BS_MATH_IEEE) return chk ? pick_f32_unroll<bsk::MATH_IEEE, true>(unroll) : pick_f32_unroll<bsk::MATH_IEEE, false>(unroll);
     return chk ? pick_f32_unroll<bsk::MATH_FAST, true>(unroll) : pick_f32_unroll<bsk::MATH_FAST, false>(unroll);
 }
-KernelF64 pick_f64(int unroll, bool chk)
+template <int MATH, bool CHK>
+KernelF64 pick_f64_unroll(int unroll)
 {
     switch (unroll) {
-    case 1: return chk ? bsk::bs_map_f64<1, true> : bsk::bs_map_f64<1, false>;
-    case 4: return chk ? bsk::bs_map_f64<4, true> : bsk::bs_map_f64<4, false>;
-    default: return chk ? bsk::bs_map_f64<2, true> : bsk::bs_map_f64<2, false>;
+    case 1: return bsk::bs_map_f64<MATH, 1, CHK>;
+    case 4: return bsk::bs_map_f64<MATH, 4, CHK>;
+    default: return bsk::bs_map_f64<MATH, 2, CHK>;
     }
+}
+KernelF64 pick_f64(int math, int unroll, bool chk)
+{
+    if (math == BS_MATH_IEEE) return chk ? pick_f64_unroll<bsk::MATH_IEEE, true>(unroll) : pick_f64_unroll<bsk::MATH_IEEE, false>(unroll);
+    return chk ? pick_f64_unroll<bsk::MATH_FAST, true>(unroll) : pick_f64_unroll<bsk::MATH_FAST, false>(unroll);
 }
 const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
 {
-    return c->fp_bytes == 4 ? (const void *)pick_f32(c->math, c->unroll, chk) : (const void *)pick_f64(c->unroll, chk);
+    return c->fp_bytes == 4 ? (const void *)pick_f32(c->math, c->unroll, chk) : (const void *)pick_f64(c->math, c->unroll, chk);
 }
 
 // Launch the Map over options [first, first+count) of the shard (first must be a multiple of 4).
@@ -202,7 +208,7 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (double *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        pick_f64(c->unroll, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
+        pick_f64(c->math, c->unroll, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
     }
 }
 

@@ -1,0 +1,196 @@
+/*
+ * bs_math_f64.h -- branch-free fp64 building blocks of the BS_MATH_FAST fp64 kernel.
+ *
+ * The fp64 Map is instruction-bound, not HBM-bound, when built from libdevice's exp()/log() and IEEE-rounded
+ * divide/sqrt (412 SASS instructions per option, profiles/r01_ncu_f64_u2_444x256.txt).  These replacements keep
+ * every result within ~2 ulp but drop the special-case handling the pricing formula cannot reach:
+ *
+ *   rcp_f64      MUFU.RCP64H seed (>= 19 good bits) + ONE cubic Newton step  x(1 + e + e^2)   -> 4 ops
+ *   rsqrt_f64    MUFU.RSQ64H seed + ONE cubic step  y(1 + e/2 + 3e^2/8)                        -> 6 ops
+ *   exp_f64      x = k ln2 + r, |r| <= ln2/2, Taylor degree 13, 2^k by exponent arithmetic; 0 below -708
+ *   log_f64      x = 2^e m, m in [1/sqrt2, sqrt2), f = (m-1)/(m+1), 2 atanh(f) to f^21
+ *
+ * Written as host+device code: on the host the hardware seeds are emulated (a reciprocal truncated to 20
+ * mantissa bits), so tests/test_math_f64.py can measure the ulp error of every block against libm and of the
+ * whole price against the oracle WITHOUT a GPU (tools/math_f64_host_check.cpp).
+ */
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define BS_HD __host__ __device__ __forceinline__
+#else
+#define BS_HD inline
+#endif
+
+namespace bsm {
+
+BS_HD double from_bits(uint64_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+BS_HD uint64_t to_bits(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+
+// ---- hardware seeds (emulated on the host with the same ~2^-20 accuracy) ---------------------------
+BS_HD double seed_rcp(double b)
+{
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+    return x;
+#else
+    return from_bits(to_bits(1.0 / from_bits(to_bits(b) & 0xffffffff00000000ull)) & 0xffffffff00000000ull);
+#endif
+}
+BS_HD double seed_rsqrt(double b)
+{
+#if defined(__CUDA_ARCH__)
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+    return x;
+#else
+    return from_bits(to_bits(1.0 / sqrt(from_bits(to_bits(b) & 0xffffffff00000000ull))) & 0xffffffff00000000ull);
+#endif
+}
+
+// 1/b for normal b: seed error e0 <= ~2^-19, after x(1+e+e^2) the error is e0^3 ~ 2^-57 plus rounding.
+BS_HD double rcp_f64(double b)
+{
+    double x = seed_rcp(b);
+    double e = fma(-b, x, 1.0);
+    double c = fma(e, e, e);
+    return fma(x, c, x);
+}
+
+// 1/sqrt(t) for normal t > 0: e = 1 - t y^2, y (1 + e/2 + 3 e^2 / 8), error (5/16) e^3 ~ 2^-59 plus rounding.
+BS_HD double rsqrt_f64(double t)
+{
+    double y = seed_rsqrt(t);
+    double a = t * y;
+    double e = fma(-a, y, 1.0);
+    double c = fma(0.375, e, 0.5);
+    double ye = y * e;
+    return fma(ye, c, y);
+}
+
+// exp(x) for x <= 0.35 or so (the Map only needs x <= 0): exact zero below -708 (no subnormal results).
+BS_HD double exp_f64(double x)
+{
+    const double L2E = 1.44269504088896338700e+00;
+    const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51: rounds to nearest integer in the low word
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    double kd = fma(x, L2E, MAGIC);
+    const int k = (int)(uint32_t)to_bits(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -LN2_HI, x);
+    r = fma(kd, -LN2_LO, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);        // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);        // 1/11!
+    p = fma(p, r, 2.7557319223985888e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);        // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);        // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    // p in [0.70, 1.42]: multiply by 2^k by adding k to the exponent field
+    const uint64_t scaled = to_bits(p) + ((uint64_t)(int64_t)k << 52);
+    return x < -708.0 ? 0.0 : from_bits(scaled);
+}
+
+// log(x) for normal x > 0.
+BS_HD double log_f64(double x)
+{
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    uint64_t b = to_bits(x);
+    int e = (int)(b >> 52) - 1023;
+    uint64_t mb = (b & 0x000fffffffffffffull) | 0x3ff0000000000000ull;  // m in [1, 2)
+    const bool upper = mb >= 0x3ff6a09e667f3bcdull;                     // m >= sqrt(2): halve it
+    mb = upper ? mb - 0x0010000000000000ull : mb;
+    e = upper ? e + 1 : e;
+    const double m = from_bits(mb);
+    const double f = (m - 1.0) * rcp_f64(m + 1.0);
+    const double f2 = f * f;
+    double q = 4.7619047619047616e-02;            // 1/21
+    q = fma(q, f2, 5.2631578947368418e-02);       // 1/19
+    q = fma(q, f2, 5.8823529411764705e-02);       // 1/17
+    q = fma(q, f2, 6.6666666666666666e-02);       // 1/15
+    q = fma(q, f2, 7.6923076923076927e-02);       // 1/13
+    q = fma(q, f2, 9.0909090909090912e-02);       // 1/11
+    q = fma(q, f2, 1.1111111111111111e-01);       // 1/9
+    q = fma(q, f2, 1.4285714285714285e-01);       // 1/7
+    q = fma(q, f2, 2.0000000000000001e-01);       // 1/5
+    q = fma(q, f2, 3.3333333333333331e-01);       // 1/3
+    const double two_f = f + f;
+    const double ed = (double)e;
+    // e ln2 + 2f + 2f f^2 q, small terms first
+    double tail = fma(two_f * f2, q, ed * LN2_LO);
+    return fma(ed, LN2_HI, two_f + tail);
+}
+
+// 1 - N(|d|) given k = 1/(1 + 0.2316419|d|): n(d) poly(k), constants of CNDF (blackscholes.c:126,:156,:164-170)
+// pre-multiplied by 1/sqrt(2 pi).
+BS_HD double cndf_tail_f64(double d, double k)
+{
+    const double INV_SQRT_2PI = 0.39894228040143270286;
+    const double A1 = 0.319381530 * INV_SQRT_2PI, A2 = -0.356563782 * INV_SQRT_2PI, A3 = 1.781477937 * INV_SQRT_2PI;
+    const double A4 = -1.821255978 * INV_SQRT_2PI, A5 = 1.330274429 * INV_SQRT_2PI;
+    double e = exp_f64((-0.5 * d) * d);
+    double p = fma(k, A5, A4);
+    p = fma(k, p, A3);
+    p = fma(k, p, A2);
+    p = fma(k, p, A1);
+    return (p * k) * e;
+}
+
+// The whole option (BlkSchlsEqEuroNoDiv, blackscholes.c:190-258) for s, k, v, t > 0 finite.  `ok` is false for
+// degenerate inputs (den = v sqrt(t) not a positive normal number): the caller then uses the IEEE-order path.
+BS_HD double price_f64_fast(double s, double k, double r, double v, double t, int otype, bool *ok)
+{
+    const double y = rsqrt_f64(t);           // 1/sqrt(t)
+    const double sq = t * y;                 // sqrt(t)                       :224
+    const double den = v * sq;               // xDen                          :238
+    const double rkv = rcp_f64(k * v);       // one reciprocal serves 1/k and 1/v
+    const double inv_k = rkv * v, inv_v = rkv * k;
+    const double rden = y * inv_v;           // 1/(v sqrt t)
+    const double lg = log_f64(s * inv_k);    // log(s/k)                      :226
+    const double drift = fma(0.5 * v, v, r); // r + v^2/2                     :231-234
+    const double d1 = fma(drift, t, lg) * rden;  //                           :235-239
+    const double d2 = d1 - den;              //                               :240
+    const double fv = k * exp_f64(-r * t);   // strike exp(-r t)              :248
+    const double a1 = fma(fabs(d1), 0.2316419, 1.0), a2 = fma(fabs(d2), 0.2316419, 1.0);
+    const double rab = rcp_f64(a1 * a2);     // one reciprocal serves both CNDF arguments   :156-158
+    const double w1 = cndf_tail_f64(d1, rab * a2);
+    const double w2 = cndf_tail_f64(d2, rab * a1);
+    const bool put = otype != 0;
+    // N(x) = w for x < 0 and 1-w otherwise; a put needs N(-x)                :249-255
+    const double x1 = ((d1 < 0.0) != put) ? w1 : 1.0 - w1;
+    const double x2 = ((d2 < 0.0) != put) ? w2 : 1.0 - w2;
+    const double c = fma(s, x1, -(fv * x2));
+    *ok = (den > 1e-150) && (den < 1e150) && (s > 1e-150) && (s < 1e150) && (k > 1e-150) && (k < 1e150);
+    return put ? -c : c;
+}
+
+}  // namespace bsm

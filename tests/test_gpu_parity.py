@@ -51,14 +51,15 @@ def test_fp32_against_reference_golden(name, math, mname):
     print("fp32 %-9s %-4s max|delta| = %.3e%s" % (name, mname, worst, " (per 128 of magnitude)" if name == "edge2k" else ""))
 
 
+@pytest.mark.parametrize("math,mname", MATHS)
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_fp64_against_reference_golden(name):
+def test_fp64_against_reference_golden(name, math, mname):
     inputs, d = _golden_inputs(name, 8)
-    got, _, _ = gpu_prices(inputs, 8, num_runs=1)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=1, math=math)
     ref = _golden_prices(name, "f64")
     worst = assert_parity(got, ref, 8, name)
     exact = float(np.mean(got == ref))
-    print("fp64 %-9s max|delta| = %.3e, bit-identical on %.1f%% of rows" % (name, worst, 100 * exact))
+    print("fp64 %-9s %-4s max|delta| = %.3e, bit-identical on %.1f%% of rows" % (name, mname, worst, 100 * exact))
 
 
 @pytest.mark.parametrize("math,mname", MATHS)
@@ -69,11 +70,30 @@ def test_fp32_against_oracle_sizes(n, math, mname):
     assert_parity(got, oracle_prices(inputs, 4), 4, "n=%d/%s" % (n, mname))
 
 
+@pytest.mark.parametrize("math,mname", MATHS)
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 37, 257, 4096, 65537, 1000003])
-def test_fp64_against_oracle_sizes(n):
+def test_fp64_against_oracle_sizes(n, math, mname):
     inputs = inputgen_like(n, seed=n, dtype=np.float64)
-    got, _, _ = gpu_prices(inputs, 8, num_runs=2)
-    assert_parity(got, oracle_prices(inputs, 8), 8, "n=%d" % n)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=2, math=math)
+    assert_parity(got, oracle_prices(inputs, 8), 8, "n=%d/%s" % (n, mname))
+
+
+def test_fp64_degenerate_inputs_follow_the_reference():
+    # t = 0, v = 0, s = k with t = 0 ...: the fast path hands these to the IEEE-order path, which reproduces the
+    # reference's inf/NaN arithmetic (intrinsic value, or NaN where the reference gives NaN)
+    s = np.array([100.0, 90.0, 100.0, 100.0, 100.0, 1e-310, 100.0])
+    k = np.array([90.0, 100.0, 100.0, 90.0, 110.0, 100.0, 1e308])
+    r = np.full(7, 0.05)
+    v = np.array([0.2, 0.2, 0.2, 0.0, 0.0, 0.2, 0.2])
+    t = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0])
+    for o in (0, 1):
+        inputs = (s, k, r, v, t, np.full(7, o, np.int32))
+        ref = oracle_prices(inputs, 8)
+        for math in (host.MATH_IEEE, host.MATH_FAST):
+            got, _, _ = gpu_prices(inputs, 8, math=math)
+            assert (np.isnan(got) == np.isnan(ref)).all(), (o, math, got, ref)
+            m = ~np.isnan(ref)
+            assert np.allclose(got[m], ref[m], rtol=1e-9, atol=1e-12), (o, math, got, ref)
 
 
 @pytest.mark.parametrize("fp_bytes", [4, 8])

@@ -1,0 +1,61 @@
+"""CPU check of the fp64 fast-math building blocks (p3arsec_b200/csrc/bs_math_f64.h) before any GPU time is
+spent: the header is host+device code; on the host the MUFU seeds are emulated at the hardware's ~2^-20 accuracy.
+The GPU result itself is checked against the oracle in tests/test_gpu_parity.py."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from conftest import golden_path
+from gpu_util import FP64_ABS_FLOOR, FP64_REL_TOL, inputgen_like
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def checker(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("m64") / "math_f64_host_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tools", "math_f64_host_check.cpp"), "-lm"], check=True)
+    return exe
+
+
+def test_building_blocks_within_a_few_ulp(checker):
+    out = dict(l.split() for l in subprocess.run([checker], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert float(out["rcp"]) <= 1.0 and float(out["rsqrt"]) <= 1.5
+    assert float(out["exp"]) <= 1.5 and float(out["exp_small"]) <= 1.0
+    assert float(out["log"]) <= 3.0 and float(out["log_near_1"]) <= 3.0
+    assert float(out["exp_below_-708"]) == 0.0 and float(out["exp_0"]) == 1.0 and float(out["log_1"]) == 0.0
+
+
+def _fast_prices(checker, s, k, r, v, t, o):
+    rows = "\n".join("%.17g %.17g %.17g %.17g %.17g %d" % z for z in zip(s, k, r, v, t, o))
+    out = subprocess.run([checker, "price"], input=rows, capture_output=True, text=True, check=True).stdout.split()
+    return np.array(out[0::2], dtype=np.float64), np.array(out[1::2], dtype=np.int32)
+
+
+@pytest.mark.parametrize("name", ["hull4", "table1k", "edge2k"])
+def test_fast_fp64_price_matches_oracle_on_goldens(checker, name):
+    d = oracle_lib.load(golden_path(name, "in.txt"), 8)
+    ref = oracle_lib.price_map(d["sptprice"], d["strike"], d["rate"], d["volatility"], d["otime"], d["otype"], 8)
+    got, ok = _fast_prices(checker, d["sptprice"], d["strike"], d["rate"], d["volatility"], d["otime"], d["otype"])
+    assert ok.all()
+    delta = np.abs(got - ref)
+    assert (delta <= FP64_REL_TOL * np.abs(ref) + FP64_ABS_FLOOR).all(), (delta.max(), int(delta.argmax()))
+    print("%s: fast fp64 vs oracle max|delta| = %.3e" % (name, delta.max()))
+
+
+def test_fast_fp64_price_matches_oracle_on_random_inputs(checker):
+    s, k, r, v, t, o = inputgen_like(200000, seed=5, dtype=np.float64)
+    ref = oracle_lib.price_map(s, k, r, v, t, o, 8)
+    got, ok = _fast_prices(checker, s, k, r, v, t, o)
+    assert ok.all()
+    delta = np.abs(got - ref)
+    assert (delta <= FP64_REL_TOL * np.abs(ref) + FP64_ABS_FLOOR).all()
+    assert delta.max() < 1e-12
+
+
+def test_degenerate_inputs_are_flagged_for_the_ieee_path(checker):
+    got, ok = _fast_prices(checker, [100.0, 100.0, 0.0, 1e-300], [100.0, 100.0, 90.0, 100.0], [0.05] * 4, [0.2, 0.0, 0.2, 0.2], [0.0, 1.0, 1.0, 1.0], [0] * 4)
+    assert ok.tolist() == [0, 0, 0, 0]

@@ -1,0 +1,52 @@
+#!/usr/bin/env python3
+"""Repeat-and-interleave comparison of a few launch configurations (run under gpurun).
+
+Each round visits every configuration once (so drift and neighbours affect all alike); per configuration the
+median and the minimum over the rounds are printed.  Times are the library's CUDA-event ROI times.
+"""
+import argparse
+import os
+import statistics
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from p3arsec_b200 import host  # noqa: E402
+
+M = {"fast": host.MATH_FAST, "ieee": host.MATH_IEEE}
+CONFIGS = {
+    "fp32": [(4, "fast", 1, 256, 4), (4, "fast", 1, 128, 8), (4, "fast", 1, 256, 3), (4, "fast", 1, 256, 5), (4, "fast", 1, 256, 0),
+             (4, "fast", 2, 256, 0), (4, "fast", 2, 128, 0), (4, "fast", 2, 256, 2), (4, "fast", 1, 192, 5), (4, "fast", 1, 64, 16),
+             (4, "ieee", 1, 256, 0), (4, "ieee", 1, 256, 8), (4, "ieee", 1, 128, 0)],
+    "fp64": [(8, "fast", 1, 256, 0), (8, "fast", 1, 128, 0), (8, "fast", 2, 256, 0), (8, "fast", 2, 128, 0), (8, "fast", 1, 256, 2),
+             (8, "fast", 1, 256, 3), (8, "fast", 1, 64, 0), (8, "ieee", 1, 256, 0), (8, "ieee", 2, 256, 0)],
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="fp32")
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--rounds", type=int, default=7)
+    ap.add_argument("--runs", type=int, default=100)
+    a = ap.parse_args()
+    ctxs = []
+    for fp, m, u, t, b in CONFIGS[a.which]:
+        bs = host.BlackScholesGPU(a.n, fp_bytes=fp, host_staging=False, with_dgrefval=False, math=M[m], unroll=u,
+                                  threads_per_block=t, blocks_per_sm=b)
+        bs.fill_synthetic(0)
+        bs.run(a.runs)
+        ctxs.append(((fp, m, u, t, b), bs, []))
+    for _ in range(a.rounds):
+        for cfg, bs, times in ctxs:
+            bs.run(a.runs)
+            times.append(bs.timing()["roi_ms"] / a.runs * 1e3)
+    print("%-4s %-4s %6s %7s %6s %7s | %9s %9s | %9s %9s" % ("fp", "math", "unroll", "threads", "blk/SM", "blocks", "med us", "min us", "med GB/s", "Gopt/s"))
+    for (fp, m, u, t, b), bs, times in sorted(ctxs, key=lambda c: statistics.median(c[2])):
+        med, mn = statistics.median(times), min(times)
+        print("%-4d %-4s %6d %7d %6d %7d | %9.2f %9.2f | %9.1f %9.2f" % (fp * 8, m, u, t, b, bs.launch()["blocks"], med, mn,
+              host.bytes_per_option(fp) * a.n / med / 1e3, a.n / med / 1e3))
+        bs.close()
+
+
+if __name__ == "__main__":
+    main()
