@@ -136,37 +136,39 @@ void set_err(Shard &s, int status, const char *fmt, ...)
 typedef void (*KernelF32)(bsk::StreamsF32, size_t, bsk::ErrChk);
 typedef void (*KernelF64)(bsk::StreamsF64, size_t, bsk::ErrChk);
 
-template <int MATH, bool CHK>
-KernelF32 pick_f32_unroll(int unroll)
+// bs_gpu_config.variant bits
+enum {
+    VARIANT_PIPE = 1,   // software-pipelined loads (next trip in flight during the math)
+    VARIANT_PROBE = 2   // DIAGNOSTIC ONLY: no pricing, same seven streams (sum of the inputs is written): the
+                        // bandwidth ceiling of this traffic pattern.  Never selected by default.
+};
+
+template <typename FP, int MATH, bool CHK, bool PIPE>
+void (*pick_unroll(int unroll))(bsk::Streams<FP>, size_t, bsk::ErrChk)
 {
     switch (unroll) {
-    case 1: return bsk::bs_map_f32<MATH, 1, CHK>;
-    case 4: return bsk::bs_map_f32<MATH, 4, CHK>;
-    default: return bsk::bs_map_f32<MATH, 2, CHK>;
+    case 1: return bsk::bs_map<FP, MATH, 1, CHK, PIPE>;
+    case 4: return bsk::bs_map<FP, MATH, 4, CHK, PIPE>;
+    default: return bsk::bs_map<FP, MATH, 2, CHK, PIPE>;
     }
 }
-KernelF32 pick_f32(int math, int unroll, bool chk)
+template <typename FP>
+void (*pick_kernel(int math, int unroll, bool chk, bool pipe))(bsk::Streams<FP>, size_t, bsk::ErrChk)
 {
-    if (math == BS_MATH_IEEE) return chk ? pick_f32_unroll<bsk::MATH_IEEE, true>(unroll) : pick_f32_unroll<bsk::MATH_IEEE, false>(unroll);
-    return chk ? pick_f32_unroll<bsk::MATH_FAST, true>(unroll) : pick_f32_unroll<bsk::MATH_FAST, false>(unroll);
-}
-template <int MATH, bool CHK>
-KernelF64 pick_f64_unroll(int unroll)
-{
-    switch (unroll) {
-    case 1: return bsk::bs_map_f64<MATH, 1, CHK>;
-    case 4: return bsk::bs_map_f64<MATH, 4, CHK>;
-    default: return bsk::bs_map_f64<MATH, 2, CHK>;
+    if (math == bsk::MATH_PROBE) return unroll == 1 ? bsk::bs_map<FP, bsk::MATH_PROBE, 1, false, false> : bsk::bs_map<FP, bsk::MATH_PROBE, 2, false, false>;
+    if (math == BS_MATH_IEEE) {
+        if (chk) return pipe ? pick_unroll<FP, bsk::MATH_IEEE, true, true>(unroll) : pick_unroll<FP, bsk::MATH_IEEE, true, false>(unroll);
+        return pipe ? pick_unroll<FP, bsk::MATH_IEEE, false, true>(unroll) : pick_unroll<FP, bsk::MATH_IEEE, false, false>(unroll);
     }
+    if (chk) return pipe ? pick_unroll<FP, bsk::MATH_FAST, true, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, true, false>(unroll);
+    return pipe ? pick_unroll<FP, bsk::MATH_FAST, false, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, false, false>(unroll);
 }
-KernelF64 pick_f64(int math, int unroll, bool chk)
-{
-    if (math == BS_MATH_IEEE) return chk ? pick_f64_unroll<bsk::MATH_IEEE, true>(unroll) : pick_f64_unroll<bsk::MATH_IEEE, false>(unroll);
-    return chk ? pick_f64_unroll<bsk::MATH_FAST, true>(unroll) : pick_f64_unroll<bsk::MATH_FAST, false>(unroll);
-}
+int kernel_math(const bs_gpu_ctx *c) { return (c->variant & VARIANT_PROBE) ? (int)bsk::MATH_PROBE : c->math; }
+KernelF32 pick_f32(const bs_gpu_ctx *c, bool chk) { return pick_kernel<float>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
+KernelF64 pick_f64(const bs_gpu_ctx *c, bool chk) { return pick_kernel<double>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
 {
-    return c->fp_bytes == 4 ? (const void *)pick_f32(c->math, c->unroll, chk) : (const void *)pick_f64(c->math, c->unroll, chk);
+    return c->fp_bytes == 4 ? (const void *)pick_f32(c, chk) : (const void *)pick_f64(c, chk);
 }
 
 // Launch the Map over options [first, first+count) of the shard (first must be a multiple of 4).
@@ -197,7 +199,7 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (float *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const float *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        pick_f32(c->math, c->unroll, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
+        pick_f32(c, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
     } else {
         bsk::StreamsF64 a;
         a.spt = (const double *)s.d[BS_BUF_SPTPRICE] + first;
@@ -208,7 +210,7 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (double *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        pick_f64(c->math, c->unroll, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
+        pick_f64(c, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
     }
 }
 
@@ -663,6 +665,8 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (cfg->threads_per_block != 0 && (cfg->threads_per_block < 32 || cfg->threads_per_block > 256 || cfg->threads_per_block % 32))
         return BS_GPU_ERR_INVALID;
     if (cfg->blocks_per_sm < 0 || cfg->blocks_per_sm > 32) return BS_GPU_ERR_INVALID;
+    if (cfg->variant < 0 || cfg->variant > 3) return BS_GPU_ERR_INVALID;
+    if ((cfg->variant & VARIANT_PIPE) && cfg->unroll == 4) return BS_GPU_ERR_INVALID;  // would spill: not built for use
     if (cfg->num_options > 2147483647ull) return BS_GPU_ERR_INVALID;  // the reference's `int numOptions`
 
     const int have = bs_gpu_device_count();

@@ -32,7 +32,7 @@
 
 namespace bsk {
 
-enum { MATH_IEEE = 1, MATH_FAST = 2 };
+enum { MATH_PROBE = 0, MATH_IEEE = 1, MATH_FAST = 2 };  // MATH_PROBE: no pricing, traffic only (diagnostic)
 
 // ---------------------------------------------------------------------------------------------
 // 128-bit streaming accessors
@@ -171,6 +171,9 @@ __device__ __forceinline__ float price_ieee(float s, float k, float r, float v, 
 template <int MATH>
 __device__ __forceinline__ float price_f32(float s, float k, float r, float v, float t, int otype)
 {
+    // MATH_PROBE is a measurement aid, not a pricing mode: same seven streams, same access pattern, five adds.
+    // Its bandwidth is the ceiling of THIS traffic pattern (6 read streams : 1 write stream) on the device.
+    if (MATH == MATH_PROBE) return s + k + r + v + t + (float)otype;
     if (MATH == MATH_FAST) return price_fast(s, k, r, v, t, otype);
     return price_ieee(s, k, r, v, t, otype);
 }
@@ -221,6 +224,7 @@ __device__ __forceinline__ double price_f64(double s, double k, double r, double
 template <int MATH>
 __device__ __forceinline__ double price_f64_any(double s, double k, double r, double v, double t, int otype)
 {
+    if (MATH == MATH_PROBE) return s + k + r + v + t + (double)otype;
     if (MATH == MATH_FAST) {
         bool ok;
         const double p = bsm::price_f64_fast(s, k, r, v, t, otype, &ok);
@@ -260,167 +264,125 @@ __device__ __forceinline__ void err_flush(const ErrChk &ec, unsigned int local_b
 }
 
 // ---------------------------------------------------------------------------------------------
-// The fp32 Map kernel.  One "group" = 4 consecutive options = one 128-bit access per stream.
+// The Map kernel, one template for both precisions.
+//   group  = one 128-bit access per fp stream: 4 options (fp32, int4 of otype) or 2 options (fp64, int2)
+//   trip   = UNROLL independent groups per thread, interleaved grid-stride (group g + u*stride)
+//   PIPE   = software pipelining: the loads of trip i+1 are issued before the math of trip i, so the DRAM
+//            latency hides behind a whole trip of arithmetic instead of behind other warps only.  It matters for
+//            the instruction-heavy fp64 kernel (long_scoreboard was its top stall at 38 % active warps).
 // ---------------------------------------------------------------------------------------------
-struct StreamsF32 {
-    const float *spt, *strike, *rate, *vol, *otime;
+template <typename FP> struct VT;
+template <> struct VT<float> { typedef float4 vec; typedef int4 ivec; enum { LANES = 4, SHIFT = 2 }; };
+template <> struct VT<double> { typedef double2 vec; typedef int2 ivec; enum { LANES = 2, SHIFT = 1 }; };
+
+__device__ __forceinline__ float lane(const float4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ int lane(const int4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ double lane(const double2 &v, int i) { return i == 0 ? v.x : v.y; }
+__device__ __forceinline__ int lane(const int2 &v, int i) { return i == 0 ? v.x : v.y; }
+__device__ __forceinline__ void set_lane(float4 &v, int i, float x) { if (i == 0) v.x = x; else if (i == 1) v.y = x; else if (i == 2) v.z = x; else v.w = x; }
+__device__ __forceinline__ void set_lane(double2 &v, int i, double x) { if (i == 0) v.x = x; else v.y = x; }
+
+template <typename FP>
+struct Streams {
+    const FP *spt, *strike, *rate, *vol, *otime;
     const int *otype;
-    float *prices;
-    const float *refval;  // DGrefval stream, only read when CHK
+    FP *prices;
+    const FP *refval;  // DGrefval stream, only read when CHK
+};
+typedef Streams<float> StreamsF32;
+typedef Streams<double> StreamsF64;
+
+template <typename FP>
+struct Group {
+    typename VT<FP>::vec s, k, r, v, t, ref;
+    typename VT<FP>::ivec o;
 };
 
-template <int MATH, int UNROLL, bool CHK>
-__global__ void __launch_bounds__(256) bs_map_f32(StreamsF32 a, size_t n, ErrChk ec)
+template <int MATH> __device__ __forceinline__ float price_any(float s, float k, float r, float v, float t, int o) { return price_f32<MATH>(s, k, r, v, t, o); }
+template <int MATH> __device__ __forceinline__ double price_any(double s, double k, double r, double v, double t, int o) { return price_f64_any<MATH>(s, k, r, v, t, o); }
+
+template <typename FP, int MATH, int UNROLL, bool CHK, bool PIPE>
+__global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec)
 {
-    const size_t groups = n >> 2;
+    typedef typename VT<FP>::vec vec;
+    typedef typename VT<FP>::ivec ivec;
+    enum { LANES = VT<FP>::LANES, SHIFT = VT<FP>::SHIFT };
+
+    const size_t groups = n >> SHIFT;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int bad = 0;
 
-    const float4 *p_s = reinterpret_cast<const float4 *>(a.spt);
-    const float4 *p_k = reinterpret_cast<const float4 *>(a.strike);
-    const float4 *p_r = reinterpret_cast<const float4 *>(a.rate);
-    const float4 *p_v = reinterpret_cast<const float4 *>(a.vol);
-    const float4 *p_t = reinterpret_cast<const float4 *>(a.otime);
-    const int4 *p_o = reinterpret_cast<const int4 *>(a.otype);
-    const float4 *p_ref = reinterpret_cast<const float4 *>(a.refval);
-    float4 *p_out = reinterpret_cast<float4 *>(a.prices);
+    const vec *p_s = reinterpret_cast<const vec *>(a.spt);
+    const vec *p_k = reinterpret_cast<const vec *>(a.strike);
+    const vec *p_r = reinterpret_cast<const vec *>(a.rate);
+    const vec *p_v = reinterpret_cast<const vec *>(a.vol);
+    const vec *p_t = reinterpret_cast<const vec *>(a.otime);
+    const ivec *p_o = reinterpret_cast<const ivec *>(a.otype);
+    const vec *p_ref = reinterpret_cast<const vec *>(a.refval);
+    vec *p_out = reinterpret_cast<vec *>(a.prices);
 
-    // main trips: UNROLL independent groups per thread, all loads issued before any math
-    for (; g + (UNROLL - 1) * stride < groups; g += UNROLL * stride) {
-        float4 s[UNROLL], k[UNROLL], r[UNROLL], v[UNROLL], t[UNROLL], ref[UNROLL];
-        int4 o[UNROLL];
+    // all loads of a trip are issued back to back, before any of its math (group 0 of a trip is always in range)
+    auto load_trip = [&](Group<FP> *dst, size_t g0) {
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            const size_t gi = g + u * stride;
-            s[u] = ld_stream(p_s + gi);
-            k[u] = ld_stream(p_k + gi);
-            r[u] = ld_stream(p_r + gi);
-            v[u] = ld_stream(p_v + gi);
-            t[u] = ld_stream(p_t + gi);
-            o[u] = ld_stream(p_o + gi);
-            if (CHK) ref[u] = ld_stream(p_ref + gi);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const size_t gi = g + u * stride;
-            float4 p;
-            p.x = price_f32<MATH>(s[u].x, k[u].x, r[u].x, v[u].x, t[u].x, o[u].x);
-            p.y = price_f32<MATH>(s[u].y, k[u].y, r[u].y, v[u].y, t[u].y, o[u].y);
-            p.z = price_f32<MATH>(s[u].z, k[u].z, r[u].z, v[u].z, t[u].z, o[u].z);
-            p.w = price_f32<MATH>(s[u].w, k[u].w, r[u].w, v[u].w, t[u].w, o[u].w);
-            st_stream(p_out + gi, p);
-            if (CHK) {
-                if (err_bad(p.x, ref[u].x)) { bad++; err_note(ec, gi * 4 + 0); }
-                if (err_bad(p.y, ref[u].y)) { bad++; err_note(ec, gi * 4 + 1); }
-                if (err_bad(p.z, ref[u].z)) { bad++; err_note(ec, gi * 4 + 2); }
-                if (err_bad(p.w, ref[u].w)) { bad++; err_note(ec, gi * 4 + 3); }
+            const size_t gi = g0 + u * stride;
+            if (u == 0 || gi < groups) {
+                dst[u].s = ld_stream(p_s + gi);
+                dst[u].k = ld_stream(p_k + gi);
+                dst[u].r = ld_stream(p_r + gi);
+                dst[u].v = ld_stream(p_v + gi);
+                dst[u].t = ld_stream(p_t + gi);
+                dst[u].o = ld_stream(p_o + gi);
+                if (CHK) dst[u].ref = ld_stream(p_ref + gi);
             }
         }
-    }
-    // leftover whole groups (fewer than UNROLL per thread)
-    for (; g < groups; g += stride) {
-        float4 s = ld_stream(p_s + g), k = ld_stream(p_k + g), r = ld_stream(p_r + g);
-        float4 v = ld_stream(p_v + g), t = ld_stream(p_t + g);
-        int4 o = ld_stream(p_o + g);
-        float4 p;
-        p.x = price_f32<MATH>(s.x, k.x, r.x, v.x, t.x, o.x);
-        p.y = price_f32<MATH>(s.y, k.y, r.y, v.y, t.y, o.y);
-        p.z = price_f32<MATH>(s.z, k.z, r.z, v.z, t.z, o.z);
-        p.w = price_f32<MATH>(s.w, k.w, r.w, v.w, t.w, o.w);
-        st_stream(p_out + g, p);
-        if (CHK) {
-            float4 ref = ld_stream(p_ref + g);
-            if (err_bad(p.x, ref.x)) { bad++; err_note(ec, g * 4 + 0); }
-            if (err_bad(p.y, ref.y)) { bad++; err_note(ec, g * 4 + 1); }
-            if (err_bad(p.z, ref.z)) { bad++; err_note(ec, g * 4 + 2); }
-            if (err_bad(p.w, ref.w)) { bad++; err_note(ec, g * 4 + 3); }
-        }
-    }
-    // ragged tail: the last n % 4 options, one scalar option per thread of block 0
-    const size_t tail0 = groups << 2;
-    if (blockIdx.x == 0 && tail0 + threadIdx.x < n) {
-        const size_t i = tail0 + threadIdx.x;
-        float p = price_f32<MATH>(a.spt[i], a.strike[i], a.rate[i], a.vol[i], a.otime[i], a.otype[i]);
-        a.prices[i] = p;
-        if (CHK && err_bad(p, a.refval[i])) { bad++; err_note(ec, i); }
-    }
-    if (CHK) err_flush(ec, bad);
-}
-
-// ---------------------------------------------------------------------------------------------
-// The fp64 Map kernel.  One group = 2 consecutive options = one 128-bit access per fp stream
-// (64-bit for otype).
-// ---------------------------------------------------------------------------------------------
-struct StreamsF64 {
-    const double *spt, *strike, *rate, *vol, *otime;
-    const int *otype;
-    double *prices;
-    const double *refval;
-};
-
-template <int MATH, int UNROLL, bool CHK>
-__global__ void __launch_bounds__(256) bs_map_f64(StreamsF64 a, size_t n, ErrChk ec)
-{
-    const size_t groups = n >> 1;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int bad = 0;
-
-    const double2 *p_s = reinterpret_cast<const double2 *>(a.spt);
-    const double2 *p_k = reinterpret_cast<const double2 *>(a.strike);
-    const double2 *p_r = reinterpret_cast<const double2 *>(a.rate);
-    const double2 *p_v = reinterpret_cast<const double2 *>(a.vol);
-    const double2 *p_t = reinterpret_cast<const double2 *>(a.otime);
-    const int2 *p_o = reinterpret_cast<const int2 *>(a.otype);
-    const double2 *p_ref = reinterpret_cast<const double2 *>(a.refval);
-    double2 *p_out = reinterpret_cast<double2 *>(a.prices);
-
-    for (; g + (UNROLL - 1) * stride < groups; g += UNROLL * stride) {
-        double2 s[UNROLL], k[UNROLL], r[UNROLL], v[UNROLL], t[UNROLL], ref[UNROLL];
-        int2 o[UNROLL];
+    };
+    auto price_trip = [&](const Group<FP> *src, size_t g0) {
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            const size_t gi = g + u * stride;
-            s[u] = ld_stream(p_s + gi);
-            k[u] = ld_stream(p_k + gi);
-            r[u] = ld_stream(p_r + gi);
-            v[u] = ld_stream(p_v + gi);
-            t[u] = ld_stream(p_t + gi);
-            o[u] = ld_stream(p_o + gi);
-            if (CHK) ref[u] = ld_stream(p_ref + gi);
-        }
+            const size_t gi = g0 + u * stride;
+            if (u == 0 || gi < groups) {
+                vec p;
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const size_t gi = g + u * stride;
-            double2 p;
-            p.x = price_f64_any<MATH>(s[u].x, k[u].x, r[u].x, v[u].x, t[u].x, o[u].x);
-            p.y = price_f64_any<MATH>(s[u].y, k[u].y, r[u].y, v[u].y, t[u].y, o[u].y);
-            st_stream(p_out + gi, p);
-            if (CHK) {
-                if (err_bad(p.x, ref[u].x)) { bad++; err_note(ec, gi * 2 + 0); }
-                if (err_bad(p.y, ref[u].y)) { bad++; err_note(ec, gi * 2 + 1); }
+                for (int l = 0; l < LANES; l++)
+                    set_lane(p, l, price_any<MATH>(lane(src[u].s, l), lane(src[u].k, l), lane(src[u].r, l), lane(src[u].v, l),
+                                                   lane(src[u].t, l), lane(src[u].o, l)));
+                st_stream(p_out + gi, p);
+                if (CHK) {
+#pragma unroll
+                    for (int l = 0; l < LANES; l++)
+                        if (err_bad(lane(p, l), lane(src[u].ref, l))) { bad++; err_note(ec, gi * LANES + l); }
+                }
             }
         }
-    }
-    for (; g < groups; g += stride) {
-        double2 s = ld_stream(p_s + g), k = ld_stream(p_k + g), r = ld_stream(p_r + g);
-        double2 v = ld_stream(p_v + g), t = ld_stream(p_t + g);
-        int2 o = ld_stream(p_o + g);
-        double2 p;
-        p.x = price_f64_any<MATH>(s.x, k.x, r.x, v.x, t.x, o.x);
-        p.y = price_f64_any<MATH>(s.y, k.y, r.y, v.y, t.y, o.y);
-        st_stream(p_out + g, p);
-        if (CHK) {
-            double2 ref = ld_stream(p_ref + g);
-            if (err_bad(p.x, ref.x)) { bad++; err_note(ec, g * 2 + 0); }
-            if (err_bad(p.y, ref.y)) { bad++; err_note(ec, g * 2 + 1); }
+    };
+
+    if (!PIPE) {
+        for (; g < groups; g += (size_t)UNROLL * stride) {
+            Group<FP> cur[UNROLL];
+            load_trip(cur, g);
+            price_trip(cur, g);
+        }
+    } else if (g < groups) {
+        Group<FP> cur[UNROLL], nxt[UNROLL];
+        load_trip(cur, g);
+        for (;;) {
+            const size_t g_next = g + (size_t)UNROLL * stride;
+            const bool more = g_next < groups;
+            if (more) load_trip(nxt, g_next);  // in flight while this trip is priced
+            price_trip(cur, g);
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) cur[u] = nxt[u];
+            g = g_next;
         }
     }
-    const size_t tail0 = groups << 1;
+    // ragged tail: the last n % LANES options, one scalar option per thread of block 0
+    const size_t tail0 = groups << SHIFT;
     if (blockIdx.x == 0 && tail0 + threadIdx.x < n) {
         const size_t i = tail0 + threadIdx.x;
-        double p = price_f64_any<MATH>(a.spt[i], a.strike[i], a.rate[i], a.vol[i], a.otime[i], a.otype[i]);
+        FP p = price_any<MATH>(a.spt[i], a.strike[i], a.rate[i], a.vol[i], a.otime[i], a.otype[i]);
         a.prices[i] = p;
         if (CHK && err_bad(p, a.refval[i])) { bad++; err_note(ec, i); }
     }

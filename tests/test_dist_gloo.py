@@ -47,10 +47,13 @@ def test_shard_range_partitions_like_the_static_parallel_for(n, world):
 def test_two_gloo_ranks(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
-    port = _free_port()
-    cp = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
-                        capture_output=True, text=True, timeout=300)
+    for attempt in range(3):  # a probed-free port can be taken before torchrun binds it: retry on a new one
+        port = _free_port()
+        cp = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                             "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                            capture_output=True, text=True, timeout=300)
+        if cp.returncode == 0:
+            break
     assert cp.returncode == 0, cp.stdout[-2000:] + cp.stderr[-2000:]
     import json
     res = sorted((json.loads(l.split("RESULT ", 1)[1]) for l in cp.stdout.splitlines() if "RESULT " in l), key=lambda d: d["rank"])

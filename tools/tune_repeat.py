@@ -13,12 +13,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from p3arsec_b200 import host  # noqa: E402
 
 M = {"fast": host.MATH_FAST, "ieee": host.MATH_IEEE}
+# (fp_bytes, math, unroll, threads, blocks_per_sm, variant)   variant: 1 = pipelined loads, 2 = traffic probe
 CONFIGS = {
-    "fp32": [(4, "fast", 1, 256, 4), (4, "fast", 1, 128, 8), (4, "fast", 1, 256, 3), (4, "fast", 1, 256, 5), (4, "fast", 1, 256, 0),
-             (4, "fast", 2, 256, 0), (4, "fast", 2, 128, 0), (4, "fast", 2, 256, 2), (4, "fast", 1, 192, 5), (4, "fast", 1, 64, 16),
-             (4, "ieee", 1, 256, 0), (4, "ieee", 1, 256, 8), (4, "ieee", 1, 128, 0)],
-    "fp64": [(8, "fast", 1, 256, 0), (8, "fast", 1, 128, 0), (8, "fast", 2, 256, 0), (8, "fast", 2, 128, 0), (8, "fast", 1, 256, 2),
-             (8, "fast", 1, 256, 3), (8, "fast", 1, 64, 0), (8, "ieee", 1, 256, 0), (8, "ieee", 2, 256, 0)],
+    "fp32": [(4, "fast", 1, 256, 4, 0), (4, "fast", 1, 128, 8, 0), (4, "fast", 2, 256, 0, 0), (4, "fast", 1, 256, 0, 1), (4, "fast", 1, 256, 3, 1),
+             (4, "fast", 1, 128, 0, 1), (4, "fast", 1, 256, 2, 1), (4, "fast", 1, 256, 4, 2), (4, "fast", 1, 128, 8, 2), (4, "fast", 2, 256, 4, 2),
+             (4, "fast", 1, 256, 6, 2), (4, "fast", 1, 256, 8, 2),
+             (4, "ieee", 1, 256, 0, 0), (4, "ieee", 1, 256, 8, 0), (4, "ieee", 1, 256, 0, 1), (4, "ieee", 1, 128, 0, 1), (4, "ieee", 2, 256, 0, 0)],
+    "fp64": [(8, "fast", 1, 256, 0, 0), (8, "fast", 2, 256, 0, 0), (8, "fast", 1, 256, 0, 1), (8, "fast", 1, 128, 0, 1), (8, "fast", 2, 128, 0, 1),
+             (8, "fast", 2, 256, 0, 1), (8, "fast", 1, 64, 0, 1), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2),
+             (8, "ieee", 1, 256, 0, 0), (8, "ieee", 2, 256, 0, 0), (8, "ieee", 1, 256, 0, 1), (8, "ieee", 1, 128, 0, 1)],
 }
 
 
@@ -30,20 +33,21 @@ def main():
     ap.add_argument("--runs", type=int, default=100)
     a = ap.parse_args()
     ctxs = []
-    for fp, m, u, t, b in CONFIGS[a.which]:
+    for fp, m, u, t, b, var in CONFIGS[a.which]:
         bs = host.BlackScholesGPU(a.n, fp_bytes=fp, host_staging=False, with_dgrefval=False, math=M[m], unroll=u,
-                                  threads_per_block=t, blocks_per_sm=b)
+                                  threads_per_block=t, blocks_per_sm=b, variant=var)
         bs.fill_synthetic(0)
         bs.run(a.runs)
-        ctxs.append(((fp, m, u, t, b), bs, []))
+        ctxs.append(((fp, m, u, t, b, var), bs, []))
     for _ in range(a.rounds):
         for cfg, bs, times in ctxs:
             bs.run(a.runs)
             times.append(bs.timing()["roi_ms"] / a.runs * 1e3)
-    print("%-4s %-4s %6s %7s %6s %7s | %9s %9s | %9s %9s" % ("fp", "math", "unroll", "threads", "blk/SM", "blocks", "med us", "min us", "med GB/s", "Gopt/s"))
-    for (fp, m, u, t, b), bs, times in sorted(ctxs, key=lambda c: statistics.median(c[2])):
+    print("%-4s %-5s %6s %7s %6s %7s | %9s %9s | %9s %9s" % ("fp", "math", "unroll", "threads", "blk/SM", "blocks", "med us", "min us", "med GB/s", "Gopt/s"))
+    for (fp, m, u, t, b, var), bs, times in sorted(ctxs, key=lambda c: statistics.median(c[2])):
         med, mn = statistics.median(times), min(times)
-        print("%-4d %-4s %6d %7d %6d %7d | %9.2f %9.2f | %9.1f %9.2f" % (fp * 8, m, u, t, b, bs.launch()["blocks"], med, mn,
+        m = "PROBE" if var & 2 else m + ("+p" if var & 1 else "")
+        print("%-4d %-5s %6d %7d %6d %7d | %9.2f %9.2f | %9.1f %9.2f" % (fp * 8, m, u, t, b, bs.launch()["blocks"], med, mn,
               host.bytes_per_option(fp) * a.n / med / 1e3, a.n / med / 1e3))
         bs.close()
 
