@@ -95,7 +95,9 @@ int main(int argc, char **argv)
     if (nGpus > have) nGpus = have;
 
     bs_gpu_ctx *ctx = NULL;
+    const double t_init0 = now_s();
     rv = bs_gpu_init(&ctx, nGpus, (size_t)numOptions, (int)sizeof(fptype));
+    const double t_init1 = now_s();
     if (rv != BS_GPU_OK) {
         printf("ERROR: bs_gpu_init failed: %s.\n", bs_gpu_status_string(rv));
         exit(1);
@@ -190,7 +192,8 @@ int main(int argc, char **argv)
     printf("Num Errors: %d\n", (int)numError);
 #endif
     bs_gpu_fini(ctx);
-    printf("[BS_GPU] load_s=%.3f write_s=%.3f total_s=%.3f\n", t_loaded - t_begin, t_w1 - t_w0, now_s() - t_begin);
+    printf("[BS_GPU] load_s=%.3f (open_s=%.3f init_s=%.3f parse_s=%.3f) write_s=%.3f total_s=%.3f\n", t_loaded - t_begin,
+           t_init0 - t_begin, t_init1 - t_init0, t_loaded - t_init1, t_w1 - t_w0, now_s() - t_begin);
     printf("[HOOKS] Total time spent in ROI: %.3fs\n", t_roi1 - t_roi0);
     printf("[HOOKS] Terminating\n");
     return 0;

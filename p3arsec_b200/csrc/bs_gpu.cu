@@ -691,6 +691,10 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     c->unroll = cfg->unroll ? cfg->unroll : 1;
     if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST) c->cfg_blocks_per_sm = 4;
     c->variant = cfg->variant;
+    // fp64 is instruction-bound: software-pipelined loads (+10 % on B200, profiles/r01_tune_repeat_fp64.txt) unless
+    // the caller chose a geometry/variant explicitly
+    if (c->fp_bytes == 8 && !cfg->variant && !cfg->unroll && !cfg->threads_per_block && !cfg->blocks_per_sm && c->math == BS_MATH_FAST)
+        c->variant = VARIANT_PIPE;
 
     // contiguous shards; the first N % G shards take one extra option (ff static partitioner rule)
     const int G = cfg->num_gpus;

@@ -189,7 +189,12 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double x1 = ((d1 < 0.0) != put) ? w1 : 1.0 - w1;
     const double x2 = ((d2 < 0.0) != put) ? w2 : 1.0 - w2;
     const double c = fma(s, x1, -(fv * x2));
-    *ok = (den > 1e-150) && (den < 1e150) && (s > 1e-150) && (s < 1e150) && (k > 1e-150) && (k < 1e150);
+    // Domain of the blocks above: t, k*v and s/k positive normal numbers well inside the exponent range
+    // (biased exponent in [0x100, 0x6ff], i.e. 2^-767 .. 2^768).  Three integer range checks on the high words;
+    // everything else (t = 0, v = 0, s <= 0, NaN, inf, denormals) is left to the IEEE-order path.
+    const uint32_t LO = 0x10000000u, SPAN = 0x60000000u;
+    *ok = ((uint32_t)(to_bits(t) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(k * v) >> 32) - LO < SPAN) &&
+          ((uint32_t)(to_bits(s * inv_k) >> 32) - LO < SPAN);
     return put ? -c : c;
 }
 
