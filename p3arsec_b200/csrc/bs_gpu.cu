@@ -16,6 +16,8 @@
  * count % 4 != 0.)
  */
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -76,6 +78,7 @@ struct Shard {
     unsigned int list_n = 0;
     std::vector<long long> list;
     bool refval_on_device = false;
+    bool host_pinned = false;  // this device thread's page range of every host stream is cudaHostRegister'ed
     std::thread worker;
 };
 
@@ -88,7 +91,10 @@ struct bs_gpu_ctx {
     int math = BS_MATH_FAST;
     int cfg_threads = 0, cfg_blocks_per_sm = 0, unroll = 0, variant = 0;
     std::vector<Shard> shards;
-    void *host[BS_BUF_COUNT] = {nullptr};
+    void *host[BS_BUF_COUNT] = {nullptr};  // page-aligned anonymous mappings, pinned lazily by the device threads
+    size_t host_bytes[BS_BUF_COUNT] = {0};
+    bool setup_pending = false;  // CMD_SETUP was posted by bs_gpu_init and has not been waited for yet
+    int setup_status = BS_GPU_OK;
     bool inputs_dirty = true;   // host inputs newer than device copy
     bool device_valid = false;  // device inputs hold something meaningful
     // command mailbox
@@ -216,6 +222,46 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
 
 void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record) { launch_map_range(c, s, chk, record, 0, s.count); }
 
+// Page range of host stream b that device thread s pins: the pages are dealt out contiguously, without overlap,
+// at the page that contains the shard's first element (the last shard runs to the end of the mapping).
+void pin_range(const bs_gpu_ctx *c, const Shard &s, int b, size_t *lo, size_t *hi)
+{
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t eb = elem_bytes(c, b);
+    *lo = s.first * eb / page * page;
+    const bool last = (size_t)s.index + 1 == c->shards.size();
+    *hi = last ? c->host_bytes[b] : (s.first + s.count) * eb / page * page;
+}
+
+// Pin this device's share of the staging buffers (idempotent).  A failure is not fatal: copies from pageable
+// memory still work, only slower, so the flag is simply left unset and the reason kept for bs_gpu_last_error().
+void ensure_pinned(bs_gpu_ctx *c, Shard &s)
+{
+    if (s.host_pinned || (c->flags & BS_GPU_FLAG_NO_HOST_STAGING)) return;
+    s.host_pinned = true;
+    for (int b = 0; b < BS_BUF_COUNT; b++) {
+        size_t lo, hi;
+        pin_range(c, s, b, &lo, &hi);
+        if (hi <= lo) continue;
+        const cudaError_t e = cudaHostRegister((char *)c->host[b] + lo, hi - lo, cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s.err = std::string("cudaHostRegister: ") + cudaGetErrorString(e) + " (continuing with pageable copies)";
+        }
+    }
+}
+
+void unpin(bs_gpu_ctx *c, Shard &s)
+{
+    if (!s.host_pinned) return;
+    for (int b = 0; b < BS_BUF_COUNT; b++) {
+        size_t lo, hi;
+        pin_range(c, s, b, &lo, &hi);
+        if (hi > lo && cudaHostUnregister((char *)c->host[b] + lo) != cudaSuccess) cudaGetLastError();
+    }
+    s.host_pinned = false;
+}
+
 // ---- per-device commands (run on the device's own thread) ------------------------------------------
 void do_setup(bs_gpu_ctx *c, Shard &s)
 {
@@ -276,6 +322,7 @@ enum { UP_INPUTS = 1, UP_REFVAL = 2 };
 
 void do_upload(bs_gpu_ctx *c, Shard &s, int what)
 {
+    ensure_pinned(c, s);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     if (what & UP_INPUTS)
         for (int b = BS_BUF_SPTPRICE; b <= BS_BUF_OTYPE; b++) {
@@ -378,6 +425,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     const bool chk = c->arg_err_chk != 0;
     const int what = c->arg_upload_what;
     s.h2d_ms = s.roi_ms = s.d2h_ms = s.pipeline_ms = 0;
+    ensure_pinned(c, s);
     if (s.count == 0) { s.err_total = 0; s.list_n = 0; s.list.clear(); return; }
 
     // chunk boundaries: multiples of 1024 options keep every stream 16-byte aligned
@@ -470,6 +518,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
 void do_download(bs_gpu_ctx *c, Shard &s)
 {
     const size_t eb = elem_bytes(c, BS_BUF_PRICES);
+    ensure_pinned(c, s);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     SH_CUDA(cudaMemcpyAsync((char *)c->host[BS_BUF_PRICES] + s.first * eb, s.d[BS_BUF_PRICES], s.count * eb, cudaMemcpyDeviceToHost, s.stream));
     SH_CUDA(cudaEventRecord(s.ev1, s.stream));
@@ -536,6 +585,8 @@ void do_teardown(bs_gpu_ctx *c, Shard &s)
     (void)c;
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.copy_stream) cudaStreamSynchronize(s.copy_stream);
+    unpin(c, s);
     for (auto &kv : s.graphs) cudaGraphExecDestroy(kv.second);
     s.graphs.clear();
     if (s.d_table) cudaFree(s.d_table);
@@ -590,15 +641,21 @@ void device_thread(bs_gpu_ctx *c, int g)
     }
 }
 
-// Post one command to every device thread and wait for all of them.  Returns the first failure.
-int broadcast(bs_gpu_ctx *c, int cmd)
+// Post one command to every device thread (no waiting).
+void post(bs_gpu_ctx *c, int cmd)
+{
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->cmd = cmd;
+    c->pending = (int)c->shards.size();
+    c->epoch++;
+    c->cv_cmd.notify_all();
+}
+
+// Wait until every device thread has finished the posted command.  Returns the first failure.
+int wait_all(bs_gpu_ctx *c)
 {
     {
         std::unique_lock<std::mutex> lk(c->mu);
-        c->cmd = cmd;
-        c->pending = (int)c->shards.size();
-        c->epoch++;
-        c->cv_cmd.notify_all();
         c->cv_done.wait(lk, [&] { return c->pending == 0; });
     }
     for (auto &s : c->shards)
@@ -607,6 +664,31 @@ int broadcast(bs_gpu_ctx *c, int cmd)
             return s.status;
         }
     return BS_GPU_OK;
+}
+
+// bs_gpu_init posts CMD_SETUP and returns: the device contexts come up in the background while the caller
+// (the loader) fills the staging buffers.  The first later call collects the outcome; a failed setup is sticky.
+int finish_setup(bs_gpu_ctx *c)
+{
+    if (c->setup_pending) {
+        c->setup_status = wait_all(c);
+        c->setup_pending = false;
+    }
+    return c->setup_status;
+}
+
+// Post one command to every device thread and wait for all of them.  Returns the first failure.
+int broadcast(bs_gpu_ctx *c, int cmd)
+{
+    if (cmd != CMD_TEARDOWN && cmd != CMD_EXIT) {
+        const int st = finish_setup(c);
+        if (st != BS_GPU_OK) return st;
+    } else if (c->setup_pending) {
+        wait_all(c);
+        c->setup_pending = false;
+    }
+    post(c, cmd);
+    return wait_all(c);
 }
 
 double now_ms()
@@ -710,28 +792,28 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
         first += s.count;
     }
 
-    // pinned, portable host staging (north_star item 1); the loader writes SoA straight into it
+    // Host staging (north_star item 1): page-aligned anonymous memory the loader writes SoA straight into.  It is
+    // available immediately -- no CUDA context is needed to allocate it -- and every device thread pins
+    // (cudaHostRegister, portable) its own page range of every stream right before its first copy, so the
+    // pinning cost is spread over the device threads and the context creation overlaps the file parse.
     if (!(c->flags & BS_GPU_FLAG_NO_HOST_STAGING)) {
-        cudaSetDevice(c->shards[0].device);
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
         for (int b = 0; b < BS_BUF_COUNT; b++) {
-            const size_t bytes = std::max<size_t>(c->n, 1) * elem_bytes(c, b);
-            cudaError_t e = cudaHostAlloc(&c->host[b], bytes, cudaHostAllocPortable);
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                for (int k = 0; k < b; k++) cudaFreeHost(c->host[k]);
+            const size_t bytes = (std::max<size_t>(c->n, 1) * elem_bytes(c, b) + page - 1) / page * page;
+            void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (m == MAP_FAILED) {
+                for (int k = 0; k < b; k++) munmap(c->host[k], c->host_bytes[k]);
                 delete c;
                 return BS_GPU_ERR_NOMEM;
             }
+            c->host[b] = m;
+            c->host_bytes[b] = bytes;
         }
     }
 
     for (int g = 0; g < G; g++) c->shards[g].worker = std::thread(device_thread, c, g);
-    const int st = broadcast(c, CMD_SETUP);
-    if (st != BS_GPU_OK) {
-        fprintf(stderr, "bs_gpu_init: %s\n", c->err.c_str());
-        bs_gpu_fini(c);
-        return st;
-    }
+    post(c, CMD_SETUP);  // asynchronous: see finish_setup()
+    c->setup_pending = true;
     *out = c;
     return BS_GPU_OK;
 }
@@ -967,7 +1049,7 @@ void bs_gpu_fini(bs_gpu_ctx *c)
             if (s.worker.joinable()) s.worker.join();
     }
     for (int b = 0; b < BS_BUF_COUNT; b++)
-        if (c->host[b]) cudaFreeHost(c->host[b]);
+        if (c->host[b]) munmap(c->host[b], c->host_bytes[b]);
     delete c;
 }
 

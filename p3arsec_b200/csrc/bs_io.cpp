@@ -303,7 +303,7 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
     f->fd = fd;
     f->size = (size_t)st.st_size;
     if (f->size) {
-        void *m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        void *m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (m == MAP_FAILED) { close(fd); delete f; return BS_IO_ERR_OPEN; }
         f->data = (const char *)m;
         madvise(m, f->size, MADV_SEQUENTIAL | MADV_WILLNEED);

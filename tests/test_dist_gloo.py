@@ -23,7 +23,7 @@ out = {"rank": r.rank, "world": r.world, "first": first, "count": count,
        "max": r.max(10.0 + r.rank), "sum": r.sum(count)}
 r.barrier()
 r.close()
-print("RESULT " + json.dumps(out), flush=True)
+json.dump(out, open(os.path.join(%(out)r, "rank%%d.json" %% r.rank), "w"))  # one file per rank: stdout lines of two ranks can interleave
 '''
 
 
@@ -46,7 +46,7 @@ def test_shard_range_partitions_like_the_static_parallel_for(n, world):
 
 def test_two_gloo_ranks(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % {"root": ROOT})
+    script.write_text(WORKER % {"root": ROOT, "out": str(tmp_path)})
     for attempt in range(3):  # a probed-free port can be taken before torchrun binds it: retry on a new one
         port = _free_port()
         cp = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
@@ -56,7 +56,7 @@ def test_two_gloo_ranks(tmp_path):
             break
     assert cp.returncode == 0, cp.stdout[-2000:] + cp.stderr[-2000:]
     import json
-    res = sorted((json.loads(l.split("RESULT ", 1)[1]) for l in cp.stdout.splitlines() if "RESULT " in l), key=lambda d: d["rank"])
+    res = [json.load(open(tmp_path / ("rank%d.json" % r))) for r in (0, 1)]
     assert [d["rank"] for d in res] == [0, 1] and all(d["world"] == 2 for d in res)
     assert res[0]["first"] == 0 and res[0]["count"] == 500002 and res[1]["first"] == 500002 and res[1]["count"] == 500001
     assert all(d["max"] == 11.0 and d["sum"] == 1000003.0 for d in res)   # max over ranks / whole-job units

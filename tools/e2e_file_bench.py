@@ -32,7 +32,7 @@ def kv(stdout, prefix):
     out = {}
     for line in stdout.splitlines():
         if line.startswith(prefix):
-            for tok in line[len(prefix):].split():
+            for tok in line[len(prefix):].replace("(", " ").replace(")", " ").split():
                 if "=" in tok:
                     k, v = tok.split("=", 1)
                     try:
