@@ -770,8 +770,13 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     // Defaults from the round-1 sweep on B200 (profiles/r01_tune_sweep.txt): one 16-byte group per thread-trip
     // and, for the MUFU-math fp32 kernel, 4 x 256 resident threads per SM (~98 KB of loads in flight per SM)
     // sit at the top of the curve; more resident warps only add DRAM page conflicts.
-    c->unroll = cfg->unroll ? cfg->unroll : 1;
-    if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST) c->cfg_blocks_per_sm = 4;
+    // Sets whose single pass already lasts milliseconds (>= 64M options per device: the 1B-option set) are
+    // priced for seconds at a time; the board then sits at its 1000 W power cap, where two groups per trip with
+    // all resident CTAs sustain ~3 % more (6.2 TB/s, the same cap the traffic-only probe hits; profiles/
+    // r01_sustained_power_cap.txt).
+    const bool sustained = c->fp_bytes == 4 && c->math == BS_MATH_FAST && c->n / (size_t)cfg->num_gpus >= ((size_t)64 << 20);
+    c->unroll = cfg->unroll ? cfg->unroll : (sustained ? 2 : 1);
+    if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST && !sustained) c->cfg_blocks_per_sm = 4;
     c->variant = cfg->variant;
     // fp64 is instruction-bound: software-pipelined loads (+10 % on B200, profiles/r01_tune_repeat_fp64.txt) unless
     // the caller chose a geometry/variant explicitly
@@ -980,6 +985,8 @@ int bs_gpu_read_device(bs_gpu_ctx *c, int which, size_t first, size_t count, voi
 {
     if (!c || which < 0 || which >= BS_BUF_COUNT || (!dst && count)) return BS_GPU_ERR_INVALID;
     if (first > c->n || count > c->n - first) return BS_GPU_ERR_INVALID;
+    const int ready = finish_setup(c);
+    if (ready != BS_GPU_OK) return ready;
     const size_t eb = elem_bytes(c, which);
     for (auto &s : c->shards) {
         const size_t lo = std::max(first, s.first), hi = std::min(first + count, s.first + s.count);
@@ -1029,6 +1036,8 @@ int bs_gpu_get_timing(bs_gpu_ctx *c, bs_gpu_timing *out)
 int bs_gpu_get_launch(bs_gpu_ctx *c, int *math, int *threads_per_block, int *blocks)
 {
     if (!c || c->shards.empty()) return BS_GPU_ERR_INVALID;
+    const int ready = finish_setup(c);  // the grid is chosen by the device threads during setup
+    if (ready != BS_GPU_OK) return ready;
     if (math) *math = c->math;
     if (threads_per_block) *threads_per_block = c->shards[0].threads;
     if (blocks) *blocks = c->shards[0].blocks;
