@@ -222,12 +222,12 @@ __device__ __forceinline__ double price_f64(double s, double k, double r, double
 // 4e-13 worst absolute distance to the fp64 CPU build on the goldens); inputs it cannot handle (v sqrt(t) not a
 // positive normal number) take the IEEE-order path, so degenerate options behave exactly as in the reference.
 template <int MATH>
-__device__ __forceinline__ double price_f64_any(double s, double k, double r, double v, double t, int otype)
+__device__ __forceinline__ double price_f64_any(double s, double k, double r, double v, double t, int otype, const double *tab)
 {
     if (MATH == MATH_PROBE) return s + k + r + v + t + (double)otype;
     if (MATH == MATH_FAST) {
         bool ok;
-        const double p = bsm::price_f64_fast(s, k, r, v, t, otype, &ok);
+        const double p = bsm::price_f64_fast(s, k, r, v, t, otype, &ok, tab);
         if (__builtin_expect(ok, 1)) return p;
     }
     return price_f64(s, k, r, v, t, otype);
@@ -298,8 +298,8 @@ struct Group {
     typename VT<FP>::ivec o;
 };
 
-template <int MATH> __device__ __forceinline__ float price_any(float s, float k, float r, float v, float t, int o) { return price_f32<MATH>(s, k, r, v, t, o); }
-template <int MATH> __device__ __forceinline__ double price_any(double s, double k, double r, double v, double t, int o) { return price_f64_any<MATH>(s, k, r, v, t, o); }
+template <int MATH> __device__ __forceinline__ float price_any(float s, float k, float r, float v, float t, int o, const double *) { return price_f32<MATH>(s, k, r, v, t, o); }
+template <int MATH> __device__ __forceinline__ double price_any(double s, double k, double r, double v, double t, int o, const double *tab) { return price_f64_any<MATH>(s, k, r, v, t, o, tab); }
 
 template <typename FP, int MATH, int UNROLL, bool CHK, bool PIPE>
 __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec)
@@ -307,6 +307,15 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
     typedef typename VT<FP>::vec vec;
     typedef typename VT<FP>::ivec ivec;
     enum { LANES = VT<FP>::LANES, SHIFT = VT<FP>::SHIFT };
+
+    // the fp64 fast math reads two 64-entry tables (bs_math_f64.h) from shared memory; other variants carry 8 bytes
+    enum { USE_TAB = (sizeof(FP) == 8 && MATH == MATH_FAST) ? 1 : 0 };
+    __shared__ double s_tab[USE_TAB ? bsm::TAB_DOUBLES : 1];
+    if (USE_TAB) {
+        bsm::fill_tables(s_tab, (int)threadIdx.x, (int)blockDim.x);
+        __syncthreads();
+    }
+    const double *tab = s_tab;
 
     const size_t groups = n >> SHIFT;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
 #pragma unroll
                 for (int l = 0; l < LANES; l++)
                     set_lane(p, l, price_any<MATH>(lane(src[u].s, l), lane(src[u].k, l), lane(src[u].r, l), lane(src[u].v, l),
-                                                   lane(src[u].t, l), lane(src[u].o, l)));
+                                                   lane(src[u].t, l), lane(src[u].o, l), tab));
                 st_stream(p_out + gi, p);
                 if (CHK) {
 #pragma unroll
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
     const size_t tail0 = groups << SHIFT;
     if (blockIdx.x == 0 && tail0 + threadIdx.x < n) {
         const size_t i = tail0 + threadIdx.x;
-        FP p = price_any<MATH>(a.spt[i], a.strike[i], a.rate[i], a.vol[i], a.otime[i], a.otype[i]);
+        FP p = price_any<MATH>(a.spt[i], a.strike[i], a.rate[i], a.vol[i], a.otime[i], a.otype[i], tab);
         a.prices[i] = p;
         if (CHK && err_bad(p, a.refval[i])) { bad++; err_note(ec, i); }
     }

@@ -7,8 +7,11 @@
  *
  *   rcp_f64      MUFU.RCP64H seed (>= 19 good bits) + ONE cubic Newton step  x(1 + e + e^2)   -> 4 ops
  *   rsqrt_f64    MUFU.RSQ64H seed + ONE cubic step  y(1 + e/2 + 3e^2/8)                        -> 6 ops
- *   exp_f64      x = k ln2 + r, |r| <= ln2/2, Taylor degree 13, 2^k by exponent arithmetic; 0 below -708
- *   log_f64      x = 2^e m, m in [1/sqrt2, sqrt2), f = (m-1)/(m+1), 2 atanh(f) to f^21
+ *   exp_f64      x = (64k + j) ln2/64 + r, |r| <= ln2/128: 2^k * T[j] * (Taylor degree 5); 0 below -708  -> 11 ops
+ *   log_f64      x = 2^e m; r = m * RC[i] - 1 with i = top 6 mantissa bits, |r| < 2^-7:
+ *                (e ln2 + LC[i]) + log1p(r) (degree 7)                                           -> 12 ops
+ * The two 64-entry tables (bs_tables_f64.h, generated with 60-digit arithmetic by tools/gen_tables_f64.py) sit in
+ * shared memory on the device (Fp64Tables, 1.5 KB, filled once per CTA).
  *
  * Written as host+device code: on the host the hardware seeds are emulated (a reciprocal truncated to 20
  * mantissa bits), so tests/test_math_f64.py can measure the ulp error of every block against libm and of the
@@ -18,6 +21,8 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+
+#include "bs_tables_f64.h"
 
 #if defined(__CUDACC__)
 #define BS_HD __host__ __device__ __forceinline__
@@ -90,74 +95,73 @@ BS_HD double rsqrt_f64(double t)
     return fma(ye, c, y);
 }
 
-// exp(x) for x <= 0.35 or so (the Map only needs x <= 0): exact zero below -708 (no subnormal results).
-BS_HD double exp_f64(double x)
+// Layout of the table block handed to exp_f64 / log_f64: [0,64) = 2^(j/64); then 64 pairs {1/c_i, log c_i (- ln2 for
+// i >= LOG_SPLIT)}.  On the device it lives in shared memory; on the host in a static array.
+enum { TAB_EXP = 0, TAB_LOG = 64, TAB_DOUBLES = 64 + 128 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__   // the bit tables are __constant__ under nvcc: filled by the CTA, never by host code
+#else
+inline
+#endif
+void fill_tables(double *tab, int first, int step)
 {
-    const double L2E = 1.44269504088896338700e+00;
+    for (int i = first; i < TAB_DOUBLES; i += step)
+        tab[i] = from_bits(i < TAB_LOG ? EXP2_64_BITS[i] : LOG_RC_LC_BITS[(i - TAB_LOG) >> 1][(i - TAB_LOG) & 1]);
+}
+
+// exp(x) for x <= ~700 (the Map only needs x <= 0): exact zero below -708 (no subnormal results).
+BS_HD double exp_f64(double x, const double *tab)
+{
     const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51: rounds to nearest integer in the low word
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    double kd = fma(x, L2E, MAGIC);
-    const int k = (int)(uint32_t)to_bits(kd);
+    double kd = fma(x, from_bits(INV_LN2_64_BITS), MAGIC);
+    const int n = (int)(uint32_t)to_bits(kd);  // round(x * 64/ln2) = 64 k + j
     kd -= MAGIC;
-    double r = fma(kd, -LN2_HI, x);
-    r = fma(kd, -LN2_LO, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.0876756987868100e-09);        // 1/12!
-    p = fma(p, r, 2.5052108385441720e-08);        // 1/11!
-    p = fma(p, r, 2.7557319223985888e-07);        // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
-    p = fma(p, r, 2.4801587301587302e-05);        // 1/8!
-    p = fma(p, r, 1.9841269841269841e-04);        // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);        // 1/6!
-    p = fma(p, r, 8.3333333333333332e-03);        // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    // p in [0.70, 1.42]: multiply by 2^k by adding k to the exponent field
-    const uint64_t scaled = to_bits(p) + ((uint64_t)(int64_t)k << 52);
+    double r = fma(kd, -from_bits(LN2_64_HI_BITS), x);
+    r = fma(kd, -from_bits(LN2_64_LO_BITS), r);   // |r| <= ln2/128: r^6/720 < 4e-17
+    // expm1(r) = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120); the result is T + T*expm1(r) in one fma, so only the
+    // table entry's and the final rounding (<= 1 ulp together) reach the result
+    double q = 8.3333333333333332e-03;            // 1/5!
+    q = fma(q, r, 4.1666666666666664e-02);        // 1/4!
+    q = fma(q, r, 1.6666666666666666e-01);        // 1/3!
+    q = fma(q, r, 0.5);
+    const double em1 = fma(q, r * r, r);
+    const double T = tab[TAB_EXP + (n & 63)];
+    const double m = fma(T, em1, T);              // in [0.99, 2.0)
+    const uint64_t scaled = to_bits(m) + ((uint64_t)(int64_t)(n >> 6) << 52);
     return x < -708.0 ? 0.0 : from_bits(scaled);
 }
 
-// log(x) for normal x > 0.
-BS_HD double log_f64(double x)
+// log(x) for normal x > 0.  Absolute error ~1e-16 (relative to max(1, |log x|)); arguments close to 1 keep a small
+// relative error because the table entry of their interval is already reduced by ln 2 (LOG_SPLIT).
+BS_HD double log_f64(double x, const double *tab)
 {
     const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    uint64_t b = to_bits(x);
-    int e = (int)(b >> 52) - 1023;
-    uint64_t mb = (b & 0x000fffffffffffffull) | 0x3ff0000000000000ull;  // m in [1, 2)
-    const bool upper = mb >= 0x3ff6a09e667f3bcdull;                     // m >= sqrt(2): halve it
-    mb = upper ? mb - 0x0010000000000000ull : mb;
-    e = upper ? e + 1 : e;
-    const double m = from_bits(mb);
-    const double f = (m - 1.0) * rcp_f64(m + 1.0);
-    const double f2 = f * f;
-    double q = 4.7619047619047616e-02;            // 1/21
-    q = fma(q, f2, 5.2631578947368418e-02);       // 1/19
-    q = fma(q, f2, 5.8823529411764705e-02);       // 1/17
-    q = fma(q, f2, 6.6666666666666666e-02);       // 1/15
-    q = fma(q, f2, 7.6923076923076927e-02);       // 1/13
-    q = fma(q, f2, 9.0909090909090912e-02);       // 1/11
-    q = fma(q, f2, 1.1111111111111111e-01);       // 1/9
-    q = fma(q, f2, 1.4285714285714285e-01);       // 1/7
-    q = fma(q, f2, 2.0000000000000001e-01);       // 1/5
-    q = fma(q, f2, 3.3333333333333331e-01);       // 1/3
-    const double two_f = f + f;
+    const uint64_t b = to_bits(x);
+    const int i = (int)(b >> 46) & 63;            // top 6 mantissa bits: m in [1 + i/64, 1 + (i+1)/64)
+    const int e = (int)(b >> 52) - 1023 + (i >= LOG_SPLIT ? 1 : 0);
+    const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+    const double rc = tab[TAB_LOG + 2 * i], lc = tab[TAB_LOG + 2 * i + 1];
+    const double r = fma(m, rc, -1.0);            // |r| < 2^-7: r^8/8 < 2e-18
+    double q = 1.4285714285714285e-01;            //  1/7
+    q = fma(q, r, -1.6666666666666666e-01);       // -1/6
+    q = fma(q, r, 2.0000000000000001e-01);        //  1/5
+    q = fma(q, r, -0.25);                         // -1/4
+    q = fma(q, r, 3.3333333333333331e-01);        //  1/3
+    q = fma(q, r, -0.5);                          // -1/2
+    const double lp = fma(r * r, q, r);           // log1p(r)
     const double ed = (double)e;
-    // e ln2 + 2f + 2f f^2 q, small terms first
-    double tail = fma(two_f * f2, q, ed * LN2_LO);
-    return fma(ed, LN2_HI, two_f + tail);
+    return fma(ed, LN2_HI, lc + fma(ed, LN2_LO, lp));
 }
 
 // 1 - N(|d|) given k = 1/(1 + 0.2316419|d|): n(d) poly(k), constants of CNDF (blackscholes.c:126,:156,:164-170)
 // pre-multiplied by 1/sqrt(2 pi).
-BS_HD double cndf_tail_f64(double d, double k)
+BS_HD double cndf_tail_f64(double d, double k, const double *tab)
 {
     const double INV_SQRT_2PI = 0.39894228040143270286;
     const double A1 = 0.319381530 * INV_SQRT_2PI, A2 = -0.356563782 * INV_SQRT_2PI, A3 = 1.781477937 * INV_SQRT_2PI;
     const double A4 = -1.821255978 * INV_SQRT_2PI, A5 = 1.330274429 * INV_SQRT_2PI;
-    double e = exp_f64((-0.5 * d) * d);
+    double e = exp_f64((-0.5 * d) * d, tab);
     double p = fma(k, A5, A4);
     p = fma(k, p, A3);
     p = fma(k, p, A2);
@@ -167,7 +171,7 @@ BS_HD double cndf_tail_f64(double d, double k)
 
 // The whole option (BlkSchlsEqEuroNoDiv, blackscholes.c:190-258) for s, k, v, t > 0 finite.  `ok` is false for
 // degenerate inputs (den = v sqrt(t) not a positive normal number): the caller then uses the IEEE-order path.
-BS_HD double price_f64_fast(double s, double k, double r, double v, double t, int otype, bool *ok)
+BS_HD double price_f64_fast(double s, double k, double r, double v, double t, int otype, bool *ok, const double *tab)
 {
     const double y = rsqrt_f64(t);           // 1/sqrt(t)
     const double sq = t * y;                 // sqrt(t)                       :224
@@ -175,15 +179,15 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double rkv = rcp_f64(k * v);       // one reciprocal serves 1/k and 1/v
     const double inv_k = rkv * v, inv_v = rkv * k;
     const double rden = y * inv_v;           // 1/(v sqrt t)
-    const double lg = log_f64(s * inv_k);    // log(s/k)                      :226
+    const double lg = log_f64(s * inv_k, tab);  // log(s/k)                   :226
     const double drift = fma(0.5 * v, v, r); // r + v^2/2                     :231-234
     const double d1 = fma(drift, t, lg) * rden;  //                           :235-239
     const double d2 = d1 - den;              //                               :240
-    const double fv = k * exp_f64(-r * t);   // strike exp(-r t)              :248
+    const double fv = k * exp_f64(-r * t, tab);  // strike exp(-r t)          :248
     const double a1 = fma(fabs(d1), 0.2316419, 1.0), a2 = fma(fabs(d2), 0.2316419, 1.0);
     const double rab = rcp_f64(a1 * a2);     // one reciprocal serves both CNDF arguments   :156-158
-    const double w1 = cndf_tail_f64(d1, rab * a2);
-    const double w2 = cndf_tail_f64(d2, rab * a1);
+    const double w1 = cndf_tail_f64(d1, rab * a2, tab);
+    const double w2 = cndf_tail_f64(d2, rab * a1, tab);
     const bool put = otype != 0;
     // N(x) = w for x < 0 and 1-w otherwise; a put needs N(-x)                :249-255
     const double x1 = ((d1 < 0.0) != put) ? w1 : 1.0 - w1;
