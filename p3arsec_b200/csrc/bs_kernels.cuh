@@ -218,6 +218,13 @@ __device__ __forceinline__ double price_f64(double s, double k, double r, double
     return otype == 0 ? call : put;
 }
 
+// Out-of-line copy of the IEEE-order path for the (never hot) degenerate inputs of the fast kernel: keeps the hot
+// loop compact and its register allocation free of libdevice's exp/log/div slow paths.
+__device__ __noinline__ double price_f64_cold(double s, double k, double r, double v, double t, int otype)
+{
+    return price_f64(s, k, r, v, t, otype);
+}
+
 // fp64 dispatch.  MATH_FAST: bs_math_f64.h (about half the instructions; <= ~2 ulp per building block, measured
 // 4e-13 worst absolute distance to the fp64 CPU build on the goldens); inputs it cannot handle (v sqrt(t) not a
 // positive normal number) take the IEEE-order path, so degenerate options behave exactly as in the reference.
@@ -229,6 +236,7 @@ __device__ __forceinline__ double price_f64_any(double s, double k, double r, do
         bool ok;
         const double p = bsm::price_f64_fast(s, k, r, v, t, otype, &ok, tab);
         if (__builtin_expect(ok, 1)) return p;
+        return price_f64_cold(s, k, r, v, t, otype);
     }
     return price_f64(s, k, r, v, t, otype);
 }

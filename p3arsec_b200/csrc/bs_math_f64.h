@@ -13,7 +13,7 @@
  * The two 64-entry tables (bs_tables_f64.h, generated with 60-digit arithmetic by tools/gen_tables_f64.py) sit in
  * shared memory on the device (Fp64Tables, 1.5 KB, filled once per CTA).
  *
- * Written as host+device code: on the host the hardware seeds are emulated (a reciprocal truncated to 20
+ * Written as host-or-device code (device under nvcc, host under g++): on the host the hardware seeds are emulated (a reciprocal truncated to 20
  * mantissa bits), so tests/test_math_f64.py can measure the ulp error of every block against libm and of the
  * whole price against the oracle WITHOUT a GPU (tools/math_f64_host_check.cpp).
  */
@@ -25,9 +25,9 @@
 #include "bs_tables_f64.h"
 
 #if defined(__CUDACC__)
-#define BS_HD __host__ __device__ __forceinline__
+#define BS_HD __device__ __forceinline__  /* under nvcc: device code only (the tables are __constant__) */
 #else
-#define BS_HD inline
+#define BS_HD inline                      /* plain C++: the host emulation used by the CPU tests */
 #endif
 
 namespace bsm {
@@ -52,6 +52,9 @@ BS_HD uint64_t to_bits(double d)
     return b;
 #endif
 }
+
+// Scalar constant i of bs_tables_f64.h (a __constant__ bank operand / LDCU on the device).
+BS_HD double kd(int i) { return from_bits(KD_BITS[i]); }
 
 // ---- hardware seeds (emulated on the host with the same ~2^-20 accuracy) ---------------------------
 BS_HD double seed_rcp(double b)
@@ -99,12 +102,7 @@ BS_HD double rsqrt_f64(double t)
 // i >= LOG_SPLIT)}.  On the device it lives in shared memory; on the host in a static array.
 enum { TAB_EXP = 0, TAB_LOG = 64, TAB_DOUBLES = 64 + 128 };
 
-#if defined(__CUDACC__)
-__device__ __forceinline__   // the bit tables are __constant__ under nvcc: filled by the CTA, never by host code
-#else
-inline
-#endif
-void fill_tables(double *tab, int first, int step)
+BS_HD void fill_tables(double *tab, int first, int step)
 {
     for (int i = first; i < TAB_DOUBLES; i += step)
         tab[i] = from_bits(i < TAB_LOG ? EXP2_64_BITS[i] : LOG_RC_LC_BITS[(i - TAB_LOG) >> 1][(i - TAB_LOG) & 1]);
@@ -114,16 +112,15 @@ void fill_tables(double *tab, int first, int step)
 BS_HD double exp_f64(double x, const double *tab)
 {
     const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51: rounds to nearest integer in the low word
-    double kd = fma(x, from_bits(INV_LN2_64_BITS), MAGIC);
-    const int n = (int)(uint32_t)to_bits(kd);  // round(x * 64/ln2) = 64 k + j
-    kd -= MAGIC;
-    double r = fma(kd, -from_bits(LN2_64_HI_BITS), x);
-    r = fma(kd, -from_bits(LN2_64_LO_BITS), r);   // |r| <= ln2/128: r^6/720 < 4e-17
+    double nd = fma(x, kd(K_EXP_INV), MAGIC);
+    const int n = (int)(uint32_t)to_bits(nd);  // round(x * 64/ln2) = 64 k + j
+    nd -= MAGIC;
+    double r = fma(nd, -kd(K_EXP_HI), x);
+    r = fma(nd, -kd(K_EXP_LO), r);                // |r| <= ln2/128: r^6/720 < 4e-17
     // expm1(r) = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120); the result is T + T*expm1(r) in one fma, so only the
     // table entry's and the final rounding (<= 1 ulp together) reach the result
-    double q = 8.3333333333333332e-03;            // 1/5!
-    q = fma(q, r, 4.1666666666666664e-02);        // 1/4!
-    q = fma(q, r, 1.6666666666666666e-01);        // 1/3!
+    double q = fma(kd(K_EXP_C5), r, kd(K_EXP_C4));
+    q = fma(q, r, kd(K_EXP_C3));
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
     const double T = tab[TAB_EXP + (n & 63)];
@@ -136,36 +133,31 @@ BS_HD double exp_f64(double x, const double *tab)
 // relative error because the table entry of their interval is already reduced by ln 2 (LOG_SPLIT).
 BS_HD double log_f64(double x, const double *tab)
 {
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
     const uint64_t b = to_bits(x);
     const int i = (int)(b >> 46) & 63;            // top 6 mantissa bits: m in [1 + i/64, 1 + (i+1)/64)
     const int e = (int)(b >> 52) - 1023 + (i >= LOG_SPLIT ? 1 : 0);
     const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
     const double rc = tab[TAB_LOG + 2 * i], lc = tab[TAB_LOG + 2 * i + 1];
     const double r = fma(m, rc, -1.0);            // |r| < 2^-7: r^8/8 < 2e-18
-    double q = 1.4285714285714285e-01;            //  1/7
-    q = fma(q, r, -1.6666666666666666e-01);       // -1/6
-    q = fma(q, r, 2.0000000000000001e-01);        //  1/5
-    q = fma(q, r, -0.25);                         // -1/4
-    q = fma(q, r, 3.3333333333333331e-01);        //  1/3
-    q = fma(q, r, -0.5);                          // -1/2
+    double q = fma(kd(K_LOG_C7), r, kd(K_LOG_C6));  // r - r^2/2 + r^3/3 - ... + r^7/7
+    q = fma(q, r, kd(K_LOG_C5));
+    q = fma(q, r, -0.25);
+    q = fma(q, r, kd(K_LOG_C3));
+    q = fma(q, r, -0.5);
     const double lp = fma(r * r, q, r);           // log1p(r)
     const double ed = (double)e;
-    return fma(ed, LN2_HI, lc + fma(ed, LN2_LO, lp));
+    return fma(ed, kd(K_LN2_HI), lc + fma(ed, kd(K_LN2_LO), lp));
 }
 
 // 1 - N(|d|) given k = 1/(1 + 0.2316419|d|): n(d) poly(k), constants of CNDF (blackscholes.c:126,:156,:164-170)
 // pre-multiplied by 1/sqrt(2 pi).
 BS_HD double cndf_tail_f64(double d, double k, const double *tab)
 {
-    const double INV_SQRT_2PI = 0.39894228040143270286;
-    const double A1 = 0.319381530 * INV_SQRT_2PI, A2 = -0.356563782 * INV_SQRT_2PI, A3 = 1.781477937 * INV_SQRT_2PI;
-    const double A4 = -1.821255978 * INV_SQRT_2PI, A5 = 1.330274429 * INV_SQRT_2PI;
     double e = exp_f64((-0.5 * d) * d, tab);
-    double p = fma(k, A5, A4);
-    p = fma(k, p, A3);
-    p = fma(k, p, A2);
-    p = fma(k, p, A1);
+    double p = fma(k, kd(K_CNDF_A5), kd(K_CNDF_A4));
+    p = fma(k, p, kd(K_CNDF_A3));
+    p = fma(k, p, kd(K_CNDF_A2));
+    p = fma(k, p, kd(K_CNDF_A1));
     return (p * k) * e;
 }
 
@@ -184,7 +176,7 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double d1 = fma(drift, t, lg) * rden;  //                           :235-239
     const double d2 = d1 - den;              //                               :240
     const double fv = k * exp_f64(-r * t, tab);  // strike exp(-r t)          :248
-    const double a1 = fma(fabs(d1), 0.2316419, 1.0), a2 = fma(fabs(d2), 0.2316419, 1.0);
+    const double a1 = fma(fabs(d1), kd(K_CNDF_C), 1.0), a2 = fma(fabs(d2), kd(K_CNDF_C), 1.0);
     const double rab = rcp_f64(a1 * a2);     // one reciprocal serves both CNDF arguments   :156-158
     const double w1 = cndf_tail_f64(d1, rab * a2, tab);
     const double w2 = cndf_tail_f64(d2, rab * a1, tab);
