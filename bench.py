@@ -323,7 +323,7 @@ def ours(args):
     achieved = bpo * n_per_launch / (avg_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_bytes(args.workload), "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
-                "kernel": "bsk::bs_map_f%d" % (32 if fp_bytes == 4 else 64), "algorithmic_bytes_per_option": bpo,
+                "kernel": "bsk::bs_map<%s, ...>" % ("float" if fp_bytes == 4 else "double"), "algorithmic_bytes_per_option": bpo,
                 "options_per_launch": n_per_launch, "avg_launch_us": avg_launch_ms * 1e3}
 
     # ---- CPU reference beside it (rank 0, N=1 only, bounded sample) ------------------------------
