@@ -43,6 +43,20 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options);
 int bs_io_load(bs_io_file *file, int fp_bytes, size_t count, void *sptprice, void *strike, void *rate,
                void *volatility, void *otime, int *otype, void *dgrefval, void *divq, void *divs, int nthreads);
 
+/* ---- binary SoA side-car -------------------------------------------------------
+ * A ".bssoa" file holds the already parsed streams (4 KiB header, then sptprice, strike, rate, volatility, otime,
+ * otype, DGrefval, each padded to 4 KiB) so that repeat runs skip the text parse and a 1B-option set fits on disk
+ * (28 GB instead of ~62 GB of text).  bs_io_open() recognises the format by its magic: bs_io_load() then copies the
+ * streams instead of parsing (the file's fptype must equal fp_bytes, else BS_IO_ERR_READ).  A side-car written with
+ * `source_path` records that file's size and mtime; bs_io_soa_matches() tells whether it is still current. */
+int bs_io_soa_write(const char *path, int fp_bytes, size_t count, const void *sptprice, const void *strike,
+                    const void *rate, const void *volatility, const void *otime, const int *otype,
+                    const void *dgrefval, const char *source_path);
+/* 1 if `soa_path` is a side-car of `source_path` (same size and mtime) holding fp_bytes-wide streams, else 0. */
+int bs_io_soa_matches(const char *soa_path, const char *source_path, int fp_bytes);
+/* 1 if the opened file is a binary side-car, 0 if it is text. */
+int bs_io_is_soa(const bs_io_file *file);
+
 /* Close the input file (the reference's fclose at :735). */
 int bs_io_close(bs_io_file *file);
 

@@ -11,6 +11,10 @@
  * the GPUs through the C ABI of include/bs_gpu.h, and <nthreads> selects the number of GPUs (clamped
  * to the devices present) instead of the number of host worker threads.
  *
+ * Optional: with BS_GPU_SOA_CACHE=1 in the environment the parsed SoA streams are kept in a
+ * binary side-car "<inputFile>.bssoa" (validated by the input's size and mtime), which later runs copy instead of
+ * re-parsing the text; an input that already IS a .bssoa file is accepted as such.
+ *
  * Build switches mirror the reference's: -DERR_CHK (src/Makefile:53-55), -DBS_FPTYPE=double instead of
  * editing `#define fptype` (:85), -DNUM_RUNS=<n> (:87).
  */
@@ -18,6 +22,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
 
 #include "bs_gpu.h"
 #include "bs_io.h"
@@ -66,7 +72,12 @@ int main(int argc, char **argv)
     // Read input data from file
     bs_io_file *in = NULL;
     long long header = 0;
-    int rv = bs_io_open(inputFile, &in, &header);
+    const char *cache_env = getenv("BS_GPU_SOA_CACHE");
+    const bool use_cache = cache_env && cache_env[0] && cache_env[0] != '0';
+    const std::string cachePath = std::string(inputFile) + ".bssoa";
+    const char *openPath = inputFile;
+    if (use_cache && bs_io_soa_matches(cachePath.c_str(), inputFile, (int)sizeof(fptype))) openPath = cachePath.c_str();
+    int rv = bs_io_open(openPath, &in, &header);
     if (rv == BS_IO_ERR_OPEN) {
         printf("ERROR: Unable to open file `%s'.\n", inputFile);
         exit(1);
@@ -85,18 +96,18 @@ int main(int argc, char **argv)
         exit(1);
     }
 
-    // <nthreads> -> number of GPUs
-    const int have = bs_gpu_device_count();
-    if (have <= 0) {
-        printf("ERROR: no usable CUDA device (this build has no CPU path).\n");
-        exit(1);
-    }
-    int nGpus = nThreads < 1 ? 1 : nThreads;
-    if (nGpus > have) nGpus = have;
-
+    // <nthreads> -> number of GPUs (an upper bound: clamped to the devices present).  Nothing here waits for CUDA:
+    // driver initialisation, device discovery and context creation run in the background while the rows are parsed.
     bs_gpu_ctx *ctx = NULL;
     const double t_init0 = now_s();
-    rv = bs_gpu_init(&ctx, nGpus, (size_t)numOptions, (int)sizeof(fptype));
+    bs_gpu_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.struct_size = sizeof(cfg);
+    cfg.num_options = (size_t)numOptions;
+    cfg.fp_bytes = (int)sizeof(fptype);
+    cfg.num_gpus = nThreads < 1 ? 1 : nThreads;
+    cfg.flags = BS_GPU_FLAG_WITH_DGREFVAL | BS_GPU_FLAG_ASYNC_DISCOVERY;
+    rv = bs_gpu_init_ex(&ctx, &cfg);
     const double t_init1 = now_s();
     if (rv != BS_GPU_OK) {
         printf("ERROR: bs_gpu_init failed: %s.\n", bs_gpu_status_string(rv));
@@ -119,12 +130,20 @@ int main(int argc, char **argv)
         printf("ERROR: Unable to read from file `%s'.\n", inputFile);
         exit(1);
     }
+    const bool from_soa = bs_io_is_soa(in) != 0;
     rv = bs_io_close(in);
     if (rv != BS_IO_OK) {
         printf("ERROR: Unable to close file `%s'.\n", inputFile);
         exit(1);
     }
     const double t_loaded = now_s();
+    // first run with the cache enabled: write the side-car in the background while the GPUs price
+    std::thread cacheWriter;
+    if (use_cache && !from_soa)
+        cacheWriter = std::thread([&] {
+            bs_io_soa_write(cachePath.c_str(), (int)sizeof(fptype), (size_t)numOptions, sptprice, strike, rate, volatility, otime,
+                            otype, dgrefval, inputFile);
+        });
 
     printf("Num of Options: %d\n", numOptions);
     printf("Num of Runs: %d\n", NUM_RUNS);
@@ -142,6 +161,10 @@ int main(int argc, char **argv)
 #endif
     rv = bs_gpu_price(ctx, NUM_RUNS, err_chk, &numError);
     const double t_roi1 = now_s();
+    if (rv == BS_GPU_ERR_NO_DEVICE) {
+        printf("ERROR: no usable CUDA device (this build has no CPU path).\n");
+        exit(1);
+    }
     if (rv != BS_GPU_OK) {
         printf("ERROR: bs_gpu_price failed: %s (%s).\n", bs_gpu_status_string(rv), bs_gpu_last_error(ctx));
         exit(1);
@@ -150,6 +173,7 @@ int main(int argc, char **argv)
     bs_gpu_get_timing(ctx, &tm);
     printf("roi.time|%.9f\n", t_roi1 - t_roi0);
     printf("[HOOKS] Leaving ROI\n");
+    const int nGpus = bs_gpu_num_shards(ctx);
     printf("[BS_GPU] gpus=%d h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f launches=%llu\n", nGpus, tm.h2d_ms, tm.roi_ms,
            tm.d2h_ms, tm.kernel_launches);
     if (tm.roi_ms > 0)
@@ -191,6 +215,9 @@ int main(int argc, char **argv)
 #ifdef ERR_CHK
     printf("Num Errors: %d\n", (int)numError);
 #endif
+    if (cacheWriter.joinable()) cacheWriter.join();
+    printf("[BS_GPU] input: %s\n", from_soa ? (openPath == inputFile ? "binary SoA file" : "binary SoA side-car (cache hit)")
+                                            : (use_cache ? "text (side-car written)" : "text"));
     bs_gpu_fini(ctx);
     printf("[BS_GPU] load_s=%.3f (open_s=%.3f init_s=%.3f parse_s=%.3f) write_s=%.3f total_s=%.3f\n", t_loaded - t_begin,
            t_init0 - t_begin, t_init1 - t_init0, t_loaded - t_init1, t_w1 - t_w0, now_s() - t_begin);

@@ -95,6 +95,10 @@ struct bs_gpu_ctx {
     size_t host_bytes[BS_BUF_COUNT] = {0};
     bool setup_pending = false;  // CMD_SETUP was posted by bs_gpu_init and has not been waited for yet
     int setup_status = BS_GPU_OK;
+    // BS_GPU_FLAG_ASYNC_DISCOVERY: even device discovery (cuInit) runs in the background, on this thread
+    std::thread bootstrap;
+    int want_gpus = 0;
+    std::vector<int> want_devices;
     bool inputs_dirty = true;   // host inputs newer than device copy
     bool device_valid = false;  // device inputs hold something meaningful
     // command mailbox
@@ -666,10 +670,67 @@ int wait_all(bs_gpu_ctx *c)
     return BS_GPU_OK;
 }
 
+void device_thread(bs_gpu_ctx *c, int g);
+
+// Lay the shards over `G` devices (contiguous; the first N % G shards take one extra option -- the ff static
+// partitioner rule), start one thread per device and post CMD_SETUP.
+void start_devices(bs_gpu_ctx *c, int G)
+{
+    c->shards.resize(G);
+    const size_t q = c->n / G, r = c->n % G;
+    size_t first = 0;
+    for (int g = 0; g < G; g++) {
+        Shard &s = c->shards[g];
+        s.index = g;
+        s.device = c->want_devices.empty() ? g : c->want_devices[g];
+        s.first = first;
+        s.count = q + ((size_t)g < r ? 1 : 0);
+        first += s.count;
+    }
+    for (int g = 0; g < G; g++) c->shards[g].worker = std::thread(device_thread, c, g);
+    post(c, CMD_SETUP);
+}
+
+int count_devices()
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? 0 : BS_GPU_ERR_CUDA;
+    }
+    return n;
+}
+
+// Background half of an ASYNC_DISCOVERY init: cuInit, clamp the GPU count to what exists, bring the devices up.
+void bootstrap_thread(bs_gpu_ctx *c)
+{
+    const int have = count_devices();
+    if (have <= 0) {
+        c->setup_status = have < 0 ? have : BS_GPU_ERR_NO_DEVICE;
+        c->err = "no usable CUDA device";
+        return;
+    }
+    int G = std::min(c->want_gpus, have);
+    for (int g = 0; g < (int)c->want_devices.size() && g < G; g++)
+        if (c->want_devices[g] < 0 || c->want_devices[g] >= have) {
+            c->setup_status = BS_GPU_ERR_NO_DEVICE;
+            c->err = "device ordinal out of range";
+            return;
+        }
+    if ((size_t)G > std::max<size_t>(c->n, 1)) G = (int)std::max<size_t>(c->n, 1);
+    start_devices(c, G);
+    c->setup_status = wait_all(c);
+}
+
 // bs_gpu_init posts CMD_SETUP and returns: the device contexts come up in the background while the caller
 // (the loader) fills the staging buffers.  The first later call collects the outcome; a failed setup is sticky.
 int finish_setup(bs_gpu_ctx *c)
 {
+    if (c->bootstrap.joinable()) {
+        c->bootstrap.join();  // sets setup_status
+        c->setup_pending = false;
+    }
     if (c->setup_pending) {
         c->setup_status = wait_all(c);
         c->setup_pending = false;
@@ -724,16 +785,7 @@ const char *bs_gpu_status_string(int status)
     }
 }
 
-int bs_gpu_device_count(void)
-{
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? 0 : BS_GPU_ERR_CUDA;
-    }
-    return n;
-}
+int bs_gpu_device_count(void) { return count_devices(); }
 
 int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
 {
@@ -751,12 +803,15 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if ((cfg->variant & VARIANT_PIPE) && cfg->unroll == 4) return BS_GPU_ERR_INVALID;  // would spill: not built for use
     if (cfg->num_options > 2147483647ull) return BS_GPU_ERR_INVALID;  // the reference's `int numOptions`
 
-    const int have = bs_gpu_device_count();
-    if (have <= 0) return BS_GPU_ERR_NO_DEVICE;  // no CPU fallback, by design
-    if (cfg->num_gpus > have) return BS_GPU_ERR_NO_DEVICE;
-    for (int g = 0; g < cfg->num_gpus; g++) {
-        const int dev = cfg->devices ? cfg->devices[g] : g;
-        if (dev < 0 || dev >= have) return BS_GPU_ERR_NO_DEVICE;
+    const bool async_discovery = (cfg->flags & BS_GPU_FLAG_ASYNC_DISCOVERY) != 0;
+    if (!async_discovery) {
+        const int have = bs_gpu_device_count();
+        if (have <= 0) return BS_GPU_ERR_NO_DEVICE;  // no CPU fallback, by design
+        if (cfg->num_gpus > have) return BS_GPU_ERR_NO_DEVICE;
+        for (int g = 0; g < cfg->num_gpus; g++) {
+            const int dev = cfg->devices ? cfg->devices[g] : g;
+            if (dev < 0 || dev >= have) return BS_GPU_ERR_NO_DEVICE;
+        }
     }
 
     bs_gpu_ctx *c = new (std::nothrow) bs_gpu_ctx();
@@ -783,19 +838,8 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (c->fp_bytes == 8 && !cfg->variant && !cfg->unroll && !cfg->threads_per_block && !cfg->blocks_per_sm && c->math == BS_MATH_FAST)
         c->variant = VARIANT_PIPE;
 
-    // contiguous shards; the first N % G shards take one extra option (ff static partitioner rule)
-    const int G = cfg->num_gpus;
-    c->shards.resize(G);
-    const size_t q = c->n / G, r = c->n % G;
-    size_t first = 0;
-    for (int g = 0; g < G; g++) {
-        Shard &s = c->shards[g];
-        s.index = g;
-        s.device = cfg->devices ? cfg->devices[g] : g;
-        s.first = first;
-        s.count = q + ((size_t)g < r ? 1 : 0);
-        first += s.count;
-    }
+    c->want_gpus = cfg->num_gpus;
+    if (cfg->devices) c->want_devices.assign(cfg->devices, cfg->devices + cfg->num_gpus);
 
     // Host staging (north_star item 1): page-aligned anonymous memory the loader writes SoA straight into.  It is
     // available immediately -- no CUDA context is needed to allocate it -- and every device thread pins
@@ -816,9 +860,12 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
         }
     }
 
-    for (int g = 0; g < G; g++) c->shards[g].worker = std::thread(device_thread, c, g);
-    post(c, CMD_SETUP);  // asynchronous: see finish_setup()
-    c->setup_pending = true;
+    if (async_discovery) {
+        c->bootstrap = std::thread(bootstrap_thread, c);  // cuInit + device bring-up entirely off the caller's thread
+    } else {
+        start_devices(c, cfg->num_gpus);  // asynchronous from here on: see finish_setup()
+        c->setup_pending = true;
+    }
     *out = c;
     return BS_GPU_OK;
 }
@@ -844,6 +891,7 @@ void *bs_gpu_host_buffer(bs_gpu_ctx *c, int which)
 int bs_gpu_mark_dirty(bs_gpu_ctx *c)
 {
     if (!c) return BS_GPU_ERR_INVALID;
+    finish_setup(c);
     c->inputs_dirty = true;
     for (auto &s : c->shards) s.refval_on_device = false;
     return BS_GPU_OK;
@@ -889,6 +937,10 @@ int bs_gpu_upload(bs_gpu_ctx *c)
 int bs_gpu_run(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *num_errors)
 {
     if (!c || num_runs < 0) return BS_GPU_ERR_INVALID;
+    {
+        const int ready = finish_setup(c);
+        if (ready != BS_GPU_OK) return ready;
+    }
     if (!c->device_valid) return fail(c, BS_GPU_ERR_STATE, "no inputs on the device: call bs_gpu_upload / bs_gpu_fill_synthetic first");
     if (err_chk) {
         if (!(c->flags & BS_GPU_FLAG_WITH_DGREFVAL)) return fail(c, BS_GPU_ERR_STATE, "err_chk needs BS_GPU_FLAG_WITH_DGREFVAL");
@@ -935,6 +987,10 @@ int bs_gpu_download(bs_gpu_ctx *c)
 int bs_gpu_price(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *num_errors)
 {
     if (!c || num_runs < 0) return BS_GPU_ERR_INVALID;
+    {
+        const int ready = finish_setup(c);
+        if (ready != BS_GPU_OK) return ready;
+    }
     if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "bs_gpu_price needs host staging; use bs_gpu_run");
     if (err_chk && !(c->flags & BS_GPU_FLAG_WITH_DGREFVAL)) return fail(c, BS_GPU_ERR_STATE, "err_chk needs BS_GPU_FLAG_WITH_DGREFVAL");
     const bool need_refval = err_chk && refval_missing(c);
@@ -1006,6 +1062,7 @@ int bs_gpu_read_device(bs_gpu_ctx *c, int which, size_t first, size_t count, voi
 long long bs_gpu_errors(bs_gpu_ctx *c, long long *idx, size_t cap)
 {
     if (!c || (!idx && cap)) return BS_GPU_ERR_INVALID;
+    finish_setup(c);
     size_t w = 0;
     for (auto &s : c->shards)
         for (long long local : s.list) {
@@ -1015,11 +1072,18 @@ long long bs_gpu_errors(bs_gpu_ctx *c, long long *idx, size_t cap)
     return (long long)w;
 }
 
-int bs_gpu_num_shards(bs_gpu_ctx *c) { return c ? (int)c->shards.size() : BS_GPU_ERR_INVALID; }
+int bs_gpu_num_shards(bs_gpu_ctx *c)
+{
+    if (!c) return BS_GPU_ERR_INVALID;
+    const int ready = finish_setup(c);  // with ASYNC_DISCOVERY the shard count is known only after discovery
+    return ready != BS_GPU_OK ? ready : (int)c->shards.size();
+}
 
 int bs_gpu_shard(bs_gpu_ctx *c, int g, int *device, size_t *first, size_t *count)
 {
-    if (!c || g < 0 || g >= (int)c->shards.size()) return BS_GPU_ERR_INVALID;
+    if (!c) return BS_GPU_ERR_INVALID;
+    finish_setup(c);
+    if (g < 0 || g >= (int)c->shards.size()) return BS_GPU_ERR_INVALID;
     if (device) *device = c->shards[g].device;
     if (first) *first = c->shards[g].first;
     if (count) *count = c->shards[g].count;
@@ -1035,9 +1099,10 @@ int bs_gpu_get_timing(bs_gpu_ctx *c, bs_gpu_timing *out)
 
 int bs_gpu_get_launch(bs_gpu_ctx *c, int *math, int *threads_per_block, int *blocks)
 {
-    if (!c || c->shards.empty()) return BS_GPU_ERR_INVALID;
+    if (!c) return BS_GPU_ERR_INVALID;
     const int ready = finish_setup(c);  // the grid is chosen by the device threads during setup
     if (ready != BS_GPU_OK) return ready;
+    if (c->shards.empty()) return BS_GPU_ERR_STATE;
     if (math) *math = c->math;
     if (threads_per_block) *threads_per_block = c->shards[0].threads;
     if (blocks) *blocks = c->shards[0].blocks;
@@ -1049,6 +1114,7 @@ const char *bs_gpu_last_error(bs_gpu_ctx *c) { return c ? c->err.c_str() : ""; }
 void bs_gpu_fini(bs_gpu_ctx *c)
 {
     if (!c) return;
+    if (c->bootstrap.joinable()) c->bootstrap.join();
     bool any = false;
     for (auto &s : c->shards) any = any || s.worker.joinable();
     if (any) {

@@ -38,7 +38,24 @@ struct bs_io_file {
     size_t size = 0;
     size_t body = 0;  // offset just past the header number
     int fd = -1;
+    bool soa = false;  // binary side-car instead of text
 };
+
+// ---- binary SoA side-car --------------------------------------------------------------------------------
+struct SoaHeader {
+    char magic[8];  // "BSSOA\1\0\0"
+    uint32_t version;
+    uint32_t fp_bytes;
+    uint64_t num_options;
+    uint64_t stream_stride;  // bytes between consecutive streams (each padded to SOA_ALIGN)
+    uint64_t src_size;       // size / mtime of the text file this was parsed from (0 = generated)
+    uint64_t src_mtime_ns;
+    uint32_t has_dgrefval;
+    uint32_t reserved;
+};
+static const char SOA_MAGIC[8] = {'B', 'S', 'S', 'O', 'A', 1, 0, 0};
+static const size_t SOA_ALIGN = 4096;
+static const int SOA_STREAMS = 7;  // sptprice strike rate volatility otime otype dgrefval
 
 namespace {
 
@@ -308,6 +325,21 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
         f->data = (const char *)m;
         madvise(m, f->size, MADV_SEQUENTIAL | MADV_WILLNEED);
     }
+    if (f->size >= sizeof(SoaHeader) && memcmp(f->data, SOA_MAGIC, 8) == 0) {
+        SoaHeader h;
+        memcpy(&h, f->data, sizeof(h));
+        const uint64_t need = SOA_ALIGN + h.stream_stride * SOA_STREAMS;
+        if (h.version != 1 || (h.fp_bytes != 4 && h.fp_bytes != 8) || h.num_options > 2147483647ull ||
+            h.stream_stride < h.num_options * h.fp_bytes || f->size < need) {
+            bs_io_close(f);
+            return BS_IO_ERR_READ;
+        }
+        f->soa = true;
+        f->body = SOA_ALIGN;
+        if (num_options) *num_options = (long long)h.num_options;
+        *file = f;
+        return BS_IO_OK;
+    }
     // header: fscanf("%i") == optional whitespace, then strtol(base 0)   (blackscholes.c:701)
     char head[64];
     size_t p = 0;
@@ -324,11 +356,35 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
     return BS_IO_OK;
 }
 
+static int load_soa(bs_io_file *f, int fp_bytes, size_t count, void *spt, void *strike, void *rate, void *vol, void *otime,
+                    int *otype, void *dgrefval, void *divq, void *divs, int nthreads)
+{
+    SoaHeader h;
+    memcpy(&h, f->data, sizeof(h));
+    if ((int)h.fp_bytes != fp_bytes || count > h.num_options) return BS_IO_ERR_READ;
+    if (dgrefval && !h.has_dgrefval) return BS_IO_ERR_READ;
+    void *dst[SOA_STREAMS] = {spt, strike, rate, vol, otime, otype, dgrefval};
+    const int T = host_threads(nthreads, count, 1 << 16);
+    parallel_for_chunks(T, [&](int t) {
+        const size_t lo = count * t / T, hi = count * (t + 1) / T;
+        for (int k = 0; k < SOA_STREAMS; k++) {
+            if (!dst[k]) continue;
+            const size_t eb = (k == 5) ? sizeof(int) : (size_t)fp_bytes;
+            memcpy((char *)dst[k] + lo * eb, f->data + SOA_ALIGN + h.stream_stride * k + lo * eb, (hi - lo) * eb);
+        }
+    });
+    // divq / divs are not kept (the Map never reads them; inputgen writes 0.00): report zeros
+    if (divq) memset(divq, 0, count * fp_bytes);
+    if (divs) memset(divs, 0, count * fp_bytes);
+    return BS_IO_OK;
+}
+
 int bs_io_load(bs_io_file *f, int fp_bytes, size_t count, void *spt, void *strike, void *rate, void *vol, void *otime,
                int *otype, void *dgrefval, void *divq, void *divs, int nthreads)
 {
     if (!f || (fp_bytes != 4 && fp_bytes != 8)) return BS_IO_ERR_INVALID;
     if (count && (!spt || !strike || !rate || !vol || !otime || !otype)) return BS_IO_ERR_INVALID;
+    if (f->soa) return load_soa(f, fp_bytes, count, spt, strike, rate, vol, otime, otype, dgrefval, divq, divs, nthreads);
     if (fp_bytes == 4) return load_typed<float>(f, count, spt, strike, rate, vol, otime, otype, dgrefval, divq, divs, nthreads);
     return load_typed<double>(f, count, spt, strike, rate, vol, otime, otype, dgrefval, divq, divs, nthreads);
 }
@@ -375,6 +431,66 @@ int bs_io_write_prices(const char *path, int fp_bytes, size_t count, const void 
             if (used[t] && fwrite(text[t].data(), 1, used[t], file) != used[t]) { fclose(file); return BS_IO_ERR_WRITE; }
     }
     return fclose(file) == 0 ? BS_IO_OK : BS_IO_ERR_CLOSE;
+}
+
+int bs_io_is_soa(const bs_io_file *f) { return f && f->soa ? 1 : 0; }
+
+int bs_io_soa_write(const char *path, int fp_bytes, size_t count, const void *spt, const void *strike, const void *rate,
+                    const void *vol, const void *otime, const int *otype, const void *dgrefval, const char *source_path)
+{
+    if (!path || (fp_bytes != 4 && fp_bytes != 8)) return BS_IO_ERR_INVALID;
+    if (count && (!spt || !strike || !rate || !vol || !otime || !otype)) return BS_IO_ERR_INVALID;
+    SoaHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, SOA_MAGIC, 8);
+    h.version = 1;
+    h.fp_bytes = (uint32_t)fp_bytes;
+    h.num_options = count;
+    h.stream_stride = (count * (size_t)fp_bytes + SOA_ALIGN - 1) / SOA_ALIGN * SOA_ALIGN;
+    h.has_dgrefval = dgrefval ? 1 : 0;
+    if (source_path) {
+        struct stat st;
+        if (stat(source_path, &st) != 0) return BS_IO_ERR_OPEN;
+        h.src_size = (uint64_t)st.st_size;
+        h.src_mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    }
+    // written under a temporary name and renamed, so a reader never sees a half-written side-car
+    const std::string tmp = std::string(path) + ".tmp";
+    const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return BS_IO_ERR_OPEN;
+    std::vector<char> head(SOA_ALIGN, 0);
+    memcpy(head.data(), &h, sizeof(h));
+    bool ok = pwrite(fd, head.data(), SOA_ALIGN, 0) == (ssize_t)SOA_ALIGN;
+    const void *src[SOA_STREAMS] = {spt, strike, rate, vol, otime, otype, dgrefval};
+    for (int k = 0; k < SOA_STREAMS && ok; k++) {
+        const size_t eb = (k == 5) ? sizeof(int) : (size_t)fp_bytes;
+        size_t left = src[k] ? count * eb : 0, done = 0;
+        while (left && ok) {
+            const ssize_t w = pwrite(fd, (const char *)src[k] + done, std::min<size_t>(left, (size_t)1 << 30),
+                                     (off_t)(SOA_ALIGN + h.stream_stride * k + done));
+            if (w <= 0) ok = false; else { done += (size_t)w; left -= (size_t)w; }
+        }
+    }
+    ok = ok && ftruncate(fd, (off_t)(SOA_ALIGN + h.stream_stride * SOA_STREAMS)) == 0;
+    if (close(fd) != 0) ok = false;
+    if (!ok) { unlink(tmp.c_str()); return BS_IO_ERR_WRITE; }
+    if (rename(tmp.c_str(), path) != 0) { unlink(tmp.c_str()); return BS_IO_ERR_WRITE; }
+    return BS_IO_OK;
+}
+
+int bs_io_soa_matches(const char *soa_path, const char *source_path, int fp_bytes)
+{
+    if (!soa_path || !source_path) return 0;
+    struct stat st;
+    if (stat(source_path, &st) != 0) return 0;
+    const int fd = open(soa_path, O_RDONLY);
+    if (fd < 0) return 0;
+    SoaHeader h;
+    const bool got = read(fd, &h, sizeof(h)) == (ssize_t)sizeof(h);
+    close(fd);
+    if (!got || memcmp(h.magic, SOA_MAGIC, 8) != 0 || h.version != 1 || (int)h.fp_bytes != fp_bytes) return 0;
+    const uint64_t mtime = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    return (h.src_size == (uint64_t)st.st_size && h.src_mtime_ns == mtime) ? 1 : 0;
 }
 
 /* Exposed for tests: format one value the way the writer does.  Returns the length (without NUL). */

@@ -23,7 +23,7 @@ BUF_NAMES = ("sptprice", "strike", "rate", "volatility", "otime", "otype", "pric
 # enum bs_gpu_math
 MATH_DEFAULT, MATH_IEEE, MATH_FAST = 0, 1, 2
 # flags
-FLAG_NO_HOST_STAGING, FLAG_WITH_DGREFVAL, FLAG_NO_GRAPH = 1, 2, 4
+FLAG_NO_HOST_STAGING, FLAG_WITH_DGREFVAL, FLAG_NO_GRAPH, FLAG_ASYNC_DISCOVERY = 1, 2, 4, 8
 
 NUM_RUNS = 100  # blackscholes.c:87
 
@@ -128,7 +128,7 @@ class BlackScholesGPU:
     """One bs_gpu_ctx.  `devices` is a list of CUDA ordinals (one contiguous shard each)."""
 
     def __init__(self, num_options, fp_bytes=4, devices=None, num_gpus=None, math=MATH_DEFAULT, host_staging=True,
-                 with_dgrefval=True, use_graph=True, threads_per_block=0, blocks_per_sm=0, unroll=0, variant=0):
+                 with_dgrefval=True, use_graph=True, threads_per_block=0, blocks_per_sm=0, unroll=0, variant=0, async_discovery=False):
         self._L = load_library()
         self._ctx = ctypes.c_void_p()
         if devices is None:
@@ -146,7 +146,7 @@ class BlackScholesGPU:
         cfg.num_gpus = len(self.devices)
         cfg.devices = dev_arr
         cfg.flags = (0 if host_staging else FLAG_NO_HOST_STAGING) | (FLAG_WITH_DGREFVAL if with_dgrefval else 0) | \
-                    (0 if use_graph else FLAG_NO_GRAPH)
+                    (0 if use_graph else FLAG_NO_GRAPH) | (FLAG_ASYNC_DISCOVERY if async_discovery else 0)
         cfg.math = math
         cfg.threads_per_block = threads_per_block
         cfg.blocks_per_sm = blocks_per_sm
@@ -274,7 +274,7 @@ def bytes_per_option(fp_bytes, err_chk=False):
 # ------------------------------------------------------------------------------------------------
 # include/bs_io.h -- loader / writer (blackscholes.c:696-739,:760-767 and :923-947)
 # ------------------------------------------------------------------------------------------------
-IO_SYMBOLS = ("bs_io_open", "bs_io_load", "bs_io_close", "bs_io_write_prices")
+IO_SYMBOLS = ("bs_io_open", "bs_io_load", "bs_io_close", "bs_io_write_prices", "bs_io_soa_write", "bs_io_soa_matches", "bs_io_is_soa")
 IO_ERR_OPEN, IO_ERR_READ, IO_ERR_WRITE, IO_ERR_CLOSE = -1, -2, -3, -4
 _io_ready = False
 
@@ -297,6 +297,9 @@ def _io():
         L.bs_io_close.restype, L.bs_io_close.argtypes = ci, [vp]
         L.bs_io_write_prices.restype, L.bs_io_write_prices.argtypes = ci, [ctypes.c_char_p, ci, cs, vp, ci]
         L.bs_io_format_price.restype, L.bs_io_format_price.argtypes = ci, [ctypes.c_double, ctypes.c_char_p, cs]
+        L.bs_io_soa_write.restype, L.bs_io_soa_write.argtypes = ci, [ctypes.c_char_p, ci, cs] + [vp] * 7 + [ctypes.c_char_p]
+        L.bs_io_soa_matches.restype, L.bs_io_soa_matches.argtypes = ci, [ctypes.c_char_p, ctypes.c_char_p, ci]
+        L.bs_io_is_soa.restype, L.bs_io_is_soa.argtypes = ci, [vp]
         _io_ready = True
     return L
 
@@ -345,6 +348,23 @@ def load_options(path, fp_bytes=4, into=None, nthreads=0):
         return d
     finally:
         L.bs_io_close(f)
+
+
+def write_soa(path, d, source_path=None):
+    """Write the binary SoA side-car of a loaded option set (dict as returned by load_options)."""
+    L = _io()
+    fp_bytes = d["sptprice"].dtype.itemsize
+    ptr = lambda a: np.ascontiguousarray(a).ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    ref = d.get("dgrefval")
+    st = L.bs_io_soa_write(path.encode(), fp_bytes, len(d["sptprice"]), ptr(d["sptprice"]), ptr(d["strike"]), ptr(d["rate"]),
+                           ptr(d["volatility"]), ptr(d["otime"]), ptr(d["otype"]), ptr(ref) if ref is not None else None,
+                           source_path.encode() if source_path else None)
+    if st != 0:
+        raise BsIoError(st, path)
+
+
+def soa_matches(soa_path, source_path, fp_bytes=4):
+    return bool(_io().bs_io_soa_matches(soa_path.encode(), source_path.encode(), fp_bytes))
 
 
 def write_prices(path, prices, nthreads=0):

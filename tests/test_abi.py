@@ -84,6 +84,13 @@ def test_no_cpu_fallback_without_a_gpu():
     cp = subprocess.run([exe, "1", os.path.join(ROOT, "tests", "golden", "hull4.in.txt"), "/tmp/_never.txt"],
                         capture_output=True, text=True)
     assert cp.returncode == 1 and "no usable CUDA device" in cp.stdout
+    # argument handling happens before any device is touched, exactly as in the reference driver
+    cp = subprocess.run([exe], capture_output=True, text=True)
+    assert cp.returncode == 1 and "Usage:" in cp.stdout
+    cp = subprocess.run([exe, "1", "/nonexistent/in.txt", "/tmp/_never.txt"], capture_output=True, text=True)
+    assert cp.returncode == 1 and "ERROR: Unable to open file `/nonexistent/in.txt'." in cp.stdout
+    cp = subprocess.run([exe, "9", os.path.join(ROOT, "tests", "golden", "hull4.in.txt"), "/tmp/_never.txt"], capture_output=True, text=True)
+    assert "WARNING: Not enough work, reducing number of threads to match number of options." in cp.stdout
 
 
 def test_missing_library_fails_loudly(tmp_path):

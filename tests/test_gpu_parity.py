@@ -249,6 +249,22 @@ def test_native_10m_put_call_parity_and_bounds():
     assert np.abs(call[idx] - ref).max() <= FP32_ABS_TOL
 
 
+def test_maximum_option_count_int32():
+    # the reference's `int numOptions` tops out at 2^31-1 options: 60 GB of SoA streams on one B200, device-resident
+    n = 2**31 - 1
+    with host.BlackScholesGPU(n, host_staging=False, with_dgrefval=False) as bs:
+        bs.fill_synthetic(0)
+        bs.run(2)
+        assert bs.timing()["kernel_launches"] == 2
+        ref = _golden_prices("table1k", "f32")
+        for first in (0, 1_000_000_000, n - 1999, n - 1000):      # n - 1000 covers the ragged last 3 options
+            got = bs.read_device("prices", first, 1000).astype(np.float64)
+            want = np.roll(ref, -(first % 1000))
+            assert np.abs(got - want).max() <= FP32_ABS_TOL, first
+        with pytest.raises(host.BsGpuError):
+            host.BlackScholesGPU(2**31)                            # one more does not fit an int: rejected
+
+
 def test_scaling_homogeneity():
     # price(2s, 2k) == 2 price(s, k): doubling is exact in binary floating point
     inputs = list(inputgen_like(100000, seed=12))
@@ -275,6 +291,19 @@ def test_sharded_equals_single_device():
         assert sh[0][1] == 0 and sum(c for _, _, c in sh) == n
         assert all(sh[i][1] + sh[i][2] == sh[i + 1][1] for i in range(g - 1))
         assert max(c for _, _, c in sh) - min(c for _, _, c in sh) <= 1
+
+
+def test_async_discovery_clamps_to_the_devices_present():
+    # BS_GPU_FLAG_ASYNC_DISCOVERY: init never waits for CUDA; num_gpus is an upper bound
+    inputs = inputgen_like(100003, seed=8)
+    base, _, _ = gpu_prices(inputs, 4)
+    with host.BlackScholesGPU(100003, num_gpus=64, async_discovery=True) as bs:
+        bs.set_inputs(*inputs)                      # staging buffers are usable before any device is up
+        bs.price(2)
+        assert len(bs.shards()) == min(64, host.device_count())
+        assert bs.prices.tobytes() == base.tobytes()
+    with host.BlackScholesGPU(3, num_gpus=64, async_discovery=True) as bs:
+        assert len(bs.shards()) <= 3                # never more shards than options
 
 
 # ---- the drop-in driver binary ------------------------------------------------------------------------
@@ -311,6 +340,15 @@ def test_driver_binary_err_chk_and_usage(tmp_path):
     assert len(num) == 1 and int(num[0].split()[-1]) == len(errs) and len(errs) % 100 == 0 and len(errs) > 0
     cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu")], capture_output=True, text=True)
     assert cp.returncode == 1 and "Usage:" in cp.stdout and "<nthreads> <inputFile> <outputFile>" in cp.stdout
+    # more "threads" than options: the reference's warning (blackscholes.c:707-710), then a normal run
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "64", golden_path("hull4", "in.txt"), out], capture_output=True, text=True)
+    assert cp.returncode == 0 and "WARNING: Not enough work, reducing number of threads to match number of options." in cp.stdout
+    assert_parity(np.loadtxt(out, skiprows=1), _golden_prices("hull4", "f32"), 4, "hull4 with 64 threads")
+    # an empty set is legal: header only in, header only out
+    empty = tmp_path / "empty.txt"
+    empty.write_text("0\n")
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", str(empty), out], capture_output=True, text=True)
+    assert cp.returncode == 0 and open(out).read() == "0\n"
     cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", str(tmp_path / "missing.txt"), out], capture_output=True, text=True)
     assert cp.returncode == 1 and "ERROR: Unable to open file" in cp.stdout
 
@@ -336,3 +374,21 @@ def test_reference_driver_with_cuda_map_err_chk(tmp_path):
     errs = [l for l in lines if l.startswith("Error on ")]
     num = int([l for l in lines if l.startswith("Num Errors:")][0].split()[-1])
     assert num == len(errs) and num % 100 == 0 and num >= 4800
+
+
+def test_driver_soa_cache(tmp_path):
+    import shutil
+    inp = str(tmp_path / "in.txt")
+    shutil.copy(golden_path("table1k", "in.txt"), inp)
+    env = dict(os.environ, BS_GPU_SOA_CACHE="1")
+    outs = []
+    for expect in ("text (side-car written)", "binary SoA side-car (cache hit)"):
+        out = str(tmp_path / ("p%d.txt" % len(outs)))
+        cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", inp, out], capture_output=True, text=True, env=env)
+        assert cp.returncode == 0 and ("[BS_GPU] input: " + expect) in cp.stdout, cp.stdout
+        outs.append(open(out).read())
+    assert outs[0] == outs[1] and os.path.exists(inp + ".bssoa")
+    # the side-car itself is a valid input file
+    out = str(tmp_path / "p2.txt")
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu_errchk"), "1", inp + ".bssoa", out], capture_output=True, text=True)
+    assert cp.returncode == 0 and "binary SoA file" in cp.stdout and "Num Errors: 0" in cp.stdout and open(out).read() == outs[0]

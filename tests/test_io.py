@@ -166,3 +166,44 @@ def test_empty_set(tmp_path):
     out = str(tmp_path / "o.txt")
     host.write_prices(out, np.zeros(0, np.float32))
     assert open(out).read() == "0\n"
+
+
+# ---- binary SoA side-car (include/bs_io.h) ------------------------------------------
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+def test_soa_sidecar_round_trip(fp_bytes, tmp_path):
+    src = golden_path("edge2k", "in.txt")
+    d = host.load_options(src, fp_bytes)
+    soa = str(tmp_path / "edge2k.bssoa")
+    host.write_soa(soa, d, src)
+    assert os.path.getsize(soa) % 4096 == 0
+    e = host.load_options(soa, fp_bytes)                       # bs_io_open recognises the magic
+    assert e["numOptions"] == d["numOptions"]
+    for k in ("sptprice", "strike", "rate", "volatility", "otime", "otype", "dgrefval"):
+        assert e[k].tobytes() == d[k].tobytes(), k
+    assert host.soa_matches(soa, src, fp_bytes) and not host.soa_matches(soa, src, 12 - fp_bytes)
+    assert not host.soa_matches(soa, golden_path("hull4", "in.txt"), fp_bytes)
+    with pytest.raises(host.BsIoError):                        # wrong fptype is refused, not converted
+        host.load_options(soa, 12 - fp_bytes)
+
+
+def test_soa_sidecar_goes_stale_with_its_source(tmp_path):
+    src = tmp_path / "in.txt"
+    src.write_text("1\n" + ROW + "\n")
+    d = host.load_options(str(src), 4)
+    soa = str(tmp_path / "in.txt.bssoa")
+    host.write_soa(soa, d, str(src))
+    assert host.soa_matches(soa, str(src), 4)
+    src.write_text("1\n" + ROW.replace("42.00", "43.00") + "\n")
+    os.utime(str(src), ns=(1, 1))
+    assert not host.soa_matches(soa, str(src), 4)
+    assert not host.soa_matches(str(tmp_path / "missing.bssoa"), str(src), 4)
+
+
+def test_soa_rejects_truncated_file(tmp_path):
+    d = host.load_options(golden_path("table1k", "in.txt"), 4)
+    soa = str(tmp_path / "t.bssoa")
+    host.write_soa(soa, d)
+    blob = open(soa, "rb").read()
+    open(soa, "wb").write(blob[: len(blob) // 2])
+    with pytest.raises(host.BsIoError):
+        host.load_options(soa, 4)
