@@ -181,8 +181,28 @@ const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
     return c->fp_bytes == 4 ? (const void *)pick_f32(c, chk) : (const void *)pick_f64(c, chk);
 }
 
+// One launch of the Map kernel on the shard's stream.  Unless BS_GPU_FLAG_NO_PDL is set the launch carries the
+// programmatic-stream-serialization attribute: behind another Map launch it may begin (and issue its first loads)
+// while that one drains; the kernel itself orders its stores after the predecessor (griddepcontrol.wait).  Behind
+// a copy or memset the attribute has no effect.  Captured into the runs graph as a programmatic edge.
+void launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *streams, size_t *count, bsk::ErrChk *ec, bool allow_pdl)
+{
+    void *args[3] = {streams, count, ec};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3((unsigned)s.threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (!allow_pdl || (c->flags & BS_GPU_FLAG_NO_PDL)) ? 0 : 1;
+    cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 // Launch the Map over options [first, first+count) of the shard (first must be a multiple of 4).
-void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t first, size_t count)
+void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t first, size_t count, bool allow_pdl = false)
 {
     if (count == 0) return;
     bsk::ErrChk ec;
@@ -209,7 +229,7 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (float *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const float *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        pick_f32(c, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
+        launch_kernel(c, s, (const void *)pick_f32(c, chk), blocks, &a, &count, &ec, allow_pdl);
     } else {
         bsk::StreamsF64 a;
         a.spt = (const double *)s.d[BS_BUF_SPTPRICE] + first;
@@ -220,11 +240,13 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (double *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        pick_f64(c, chk)<<<blocks, s.threads, 0, s.stream>>>(a, count, ec);
+        launch_kernel(c, s, (const void *)pick_f64(c, chk), blocks, &a, &count, &ec, allow_pdl);
     }
 }
 
-void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record) { launch_map_range(c, s, chk, record, 0, s.count); }
+// whole-shard runs follow one another on the launch stream: these are the launches that may overlap (PDL);
+// the chunk launches of a pipelined bs_gpu_price() sit behind cross-stream copy events and stay plain
+void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record) { launch_map_range(c, s, chk, record, 0, s.count, true); }
 
 // Page range of host stream b that device thread s pins: the pages are dealt out contiguously, without overlap,
 // at the page that contains the shard's first element (the last shard runs to the end of the mapping).

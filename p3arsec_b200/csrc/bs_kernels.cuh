@@ -375,15 +375,33 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
         }
     };
 
+    // Programmatic dependent launch (run j+1 of the NUM_RUNS sequence is launched with the PDL attribute): let the
+    // next run's CTAs be scheduled as soon as all of ours are running, and order OUR first store after the
+    // previous run's completion.  Our first trip of loads is issued before that wait, so the drain of run j and
+    // the fill of run j+1 overlap instead of leaving the memory system idle between launches.  Every run still
+    // reads every input and writes every price, in run order.  Both instructions are no-ops in a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (!PIPE) {
+        if (g < groups) {
+            Group<FP> cur[UNROLL];
+            load_trip(cur, g);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            price_trip(cur, g);
+            g += (size_t)UNROLL * stride;
+        } else {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
         for (; g < groups; g += (size_t)UNROLL * stride) {
             Group<FP> cur[UNROLL];
             load_trip(cur, g);
             price_trip(cur, g);
         }
-    } else if (g < groups) {
+    } else if (g >= groups) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    } else {
         Group<FP> cur[UNROLL], nxt[UNROLL];
         load_trip(cur, g);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (;;) {
             const size_t g_next = g + (size_t)UNROLL * stride;
             const bool more = g_next < groups;
