@@ -79,8 +79,9 @@ typedef enum bs_gpu_math {
 #define BS_GPU_FLAG_NO_HOST_STAGING 1u /* no pinned host buffers: device-resident data only (1B set) */
 #define BS_GPU_FLAG_WITH_DGREFVAL 2u   /* allocate the DGREFVAL stream (needed for err_chk=1)       */
 #define BS_GPU_FLAG_NO_GRAPH 4u        /* launch runs as plain stream launches, not a CUDA graph     */
-#define BS_GPU_FLAG_NO_PDL 16u         /* plain kernel-to-kernel serialisation between runs (default: programmatic
-                                          dependent launch: run j+1 is scheduled while run j drains)            */
+#define BS_GPU_FLAG_PDL 16u            /* opt-in: programmatic dependent launch between the runs (run j+1 is scheduled
+                                          and issues its first loads while run j drains; stores stay ordered).
+                                          Measured neutral to harmful on B200, hence off by default */
 #define BS_GPU_FLAG_ASYNC_DISCOVERY 8u /* bs_gpu_init_ex does not touch CUDA at all: driver initialisation and device
                                           discovery run in the background too, num_gpus is an upper bound that is
                                           clamped to the devices (and options) present, and "no device" is reported

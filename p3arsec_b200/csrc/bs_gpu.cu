@@ -181,7 +181,7 @@ const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
     return c->fp_bytes == 4 ? (const void *)pick_f32(c, chk) : (const void *)pick_f64(c, chk);
 }
 
-// One launch of the Map kernel on the shard's stream.  Unless BS_GPU_FLAG_NO_PDL is set the launch carries the
+// One launch of the Map kernel on the shard's stream.  With BS_GPU_FLAG_PDL the launch carries the
 // programmatic-stream-serialization attribute: behind another Map launch it may begin (and issue its first loads)
 // while that one drains; the kernel itself orders its stores after the predecessor (griddepcontrol.wait).  Behind
 // a copy or memset the attribute has no effect.  Captured into the runs graph as a programmatic edge.
@@ -197,7 +197,7 @@ void launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *st
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (!allow_pdl || (c->flags & BS_GPU_FLAG_NO_PDL)) ? 0 : 1;
+    cfg.numAttrs = (allow_pdl && (c->flags & BS_GPU_FLAG_PDL)) ? 1 : 0;
     cudaLaunchKernelExC(&cfg, fn, args);
 }
 

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
         }
     };
 
-    // Programmatic dependent launch (run j+1 of the NUM_RUNS sequence is launched with the PDL attribute): let the
+    // Programmatic dependent launch (opt-in, BS_GPU_FLAG_PDL: run j+1 of the NUM_RUNS sequence carries the attribute): let the
     // next run's CTAs be scheduled as soon as all of ours are running, and order OUR first store after the
     // previous run's completion.  Our first trip of loads is issued before that wait, so the drain of run j and
     // the fill of run j+1 overlap instead of leaving the memory system idle between launches.  Every run still
