@@ -79,6 +79,7 @@ typedef enum bs_gpu_math {
 #define BS_GPU_FLAG_NO_HOST_STAGING 1u /* no pinned host buffers: device-resident data only (1B set) */
 #define BS_GPU_FLAG_WITH_DGREFVAL 2u   /* allocate the DGREFVAL stream (needed for err_chk=1)       */
 #define BS_GPU_FLAG_NO_GRAPH 4u        /* launch runs as plain stream launches, not a CUDA graph     */
+#define BS_GPU_FLAG_NO_SUBSHARDS 32u   /* bs_gpu_price(): never cut a shard into sub-shards (see bs_gpu_price)        */
 #define BS_GPU_FLAG_PDL 16u            /* opt-in: programmatic dependent launch between the runs (run j+1 is scheduled
                                           and issues its first loads while run j drains; stores stay ordered).
                                           Measured neutral to harmful on B200, hence off by default */
@@ -143,9 +144,12 @@ int bs_gpu_mark_dirty(bs_gpu_ctx *ctx);
 /* The hot path.  H2D of the input streams if they are dirty, then `num_runs` real launches of the
  * pricing kernel per device (every run re-reads all inputs and rewrites all prices; nothing is
  * cached or hoisted across runs), then D2H of the prices into the pinned PRICES buffer.  Blocking.
- * Copies and launches are pipelined in run order: run 0 is launched chunk by chunk as the input
- * chunks land, runs 1..num_runs-2 are whole-set launches, and the last run is launched chunk by chunk
- * with each price chunk copied back as soon as it is complete.
+ * Copies and launches are pipelined.  A shard whose streams exceed 256 MiB is cut into contiguous sub-shards,
+ * each larger than the L2 cache (so every run over it still streams its inputs from HBM): sub-shard i runs all
+ * its num_runs launches while sub-shard i+1 is still on the PCIe bus and the prices of sub-shard i-1 travel
+ * back -- the time-multiplexed twin of sharding over several GPUs.  Smaller shards keep run order: run 0 is
+ * launched chunk by chunk as the input chunks land, runs 1..num_runs-2 are whole-shard launches, and the last
+ * run is launched chunk by chunk with each price chunk copied back as soon as it is complete.
  * With err_chk != 0 every run also evaluates |DGrefval - price| >= 1e-4 (blackscholes.c:335) and
  * *num_errors receives the total over all runs, i.e. the number the reference prints as
  * "Num Errors" (blackscholes.c:950).  num_errors may be NULL. */

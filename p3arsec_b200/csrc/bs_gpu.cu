@@ -45,7 +45,14 @@ enum { PIPE_CHUNKS = 8 };  // chunks of the first / last run of a pipelined bs_g
 
 struct GraphKey {
     int num_runs, err_chk;  // err_chk: 0 = off, 1 = on and the last run records offenders, 2 = on, nothing recorded
-    bool operator<(const GraphKey &o) const { return num_runs != o.num_runs ? num_runs < o.num_runs : err_chk < o.err_chk; }
+    size_t first, count;    // option range of the shard the launches cover
+    bool operator<(const GraphKey &o) const
+    {
+        if (num_runs != o.num_runs) return num_runs < o.num_runs;
+        if (err_chk != o.err_chk) return err_chk < o.err_chk;
+        if (first != o.first) return first < o.first;
+        return count < o.count;
+    }
 };
 
 struct Shard {
@@ -63,7 +70,8 @@ struct Shard {
     char *d_table = nullptr;  // synthetic base table, built on first fill
     // execution
     cudaStream_t stream = nullptr;       // launches (and the un-pipelined copies)
-    cudaStream_t copy_stream = nullptr;  // H2D / D2H of a pipelined bs_gpu_price()
+    cudaStream_t copy_stream = nullptr;  // H2D (and, in the chunked scheme, D2H) of a pipelined bs_gpu_price()
+    cudaStream_t d2h_stream = nullptr;   // D2H of the sub-shard scheme: the two copy engines work at the same time
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;  // timing marks of the pipeline
     cudaEvent_t ev_in[PIPE_CHUNKS] = {nullptr}, ev_out[PIPE_CHUNKS] = {nullptr};  // chunk landed / chunk priced
@@ -244,9 +252,6 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
     }
 }
 
-// whole-shard runs follow one another on the launch stream: these are the launches that may overlap (PDL);
-// the chunk launches of a pipelined bs_gpu_price() sit behind cross-stream copy events and stay plain
-void launch_map(bs_gpu_ctx *c, Shard &s, bool chk, int record) { launch_map_range(c, s, chk, record, 0, s.count, true); }
 
 // Page range of host stream b that device thread s pins: the pages are dealt out contiguously, without overlap,
 // at the page that contains the shard's first element (the last shard runs to the end of the mapping).
@@ -297,6 +302,7 @@ void do_setup(bs_gpu_ctx *c, Shard &s)
     s.sm_count = prop.multiProcessorCount;
     SH_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     SH_CUDA(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    SH_CUDA(cudaStreamCreateWithFlags(&s.d2h_stream, cudaStreamNonBlocking));
     SH_CUDA(cudaEventCreate(&s.ev0));
     SH_CUDA(cudaEventCreate(&s.ev1));
     SH_CUDA(cudaEventCreate(&s.ev_h2d));
@@ -367,10 +373,11 @@ void do_upload(bs_gpu_ctx *c, Shard &s, int what)
 }
 
 // NUM_RUNS real launches (blackscholes.c:318): every run re-reads all inputs and rewrites all prices
-void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last)
+void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last, size_t first, size_t count)
 {
-    for (int j = 0; j < num_runs; j++) launch_map(c, s, chk, chk && record_last && j == num_runs - 1);
+    for (int j = 0; j < num_runs; j++) launch_map_range(c, s, chk, chk && record_last && j == num_runs - 1, first, count, true);
 }
+void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last) { enqueue_runs(c, s, num_runs, chk, record_last, 0, s.count); }
 
 void reset_err_counters(Shard &s)
 {
@@ -378,23 +385,27 @@ void reset_err_counters(Shard &s)
     cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream);
 }
 
-// `num_runs` whole-shard launches as one cached CUDA graph (or nullptr when graphs are disabled)
-cudaGraphExec_t runs_graph(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last)
+// `num_runs` launches over [first, first+count) as one cached CUDA graph (or nullptr when graphs are disabled)
+cudaGraphExec_t runs_graph(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last, size_t first, size_t count)
 {
     if ((c->flags & BS_GPU_FLAG_NO_GRAPH) || num_runs <= 0) return nullptr;
-    GraphKey key = {num_runs, chk ? (record_last ? 1 : 2) : 0};
+    GraphKey key = {num_runs, chk ? (record_last ? 1 : 2) : 0, first, count};
     auto it = s.graphs.find(key);
     if (it != s.graphs.end()) return it->second;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return nullptr;
-    enqueue_runs(c, s, num_runs, chk, record_last);
+    enqueue_runs(c, s, num_runs, chk, record_last, first, count);
     if (cudaStreamEndCapture(s.stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return nullptr; }
     if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return nullptr; }
     cudaGraphDestroy(graph);
     cudaGraphUpload(exec, s.stream);
     s.graphs[key] = exec;
     return exec;
+}
+cudaGraphExec_t runs_graph(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last)
+{
+    return runs_graph(c, s, num_runs, chk, record_last, 0, s.count);
 }
 
 void fetch_err_results(bs_gpu_ctx *c, Shard &s, bool chk);
@@ -445,6 +456,90 @@ void fetch_err_results(bs_gpu_ctx *c, Shard &s, bool chk)
 //   launch stream : run 0 chunk 0..7 (each after its inputs landed) | runs 1..R-2 whole-shard | run R-1 chunk 0..7
 // Every run still reads every input from HBM and writes every price; only the first and the last run are
 // cut into PIPE_CHUNKS launches so that PCIe traffic hides behind them.
+// Number of sub-shards a bs_gpu_price() call cuts this shard into.  A sub-shard's streams must not fit the L2
+// (126 MB): every run over it then still streams every input from HBM -- ncu on a 5M-option (140 MB) sub-shard:
+// dram__bytes_read = 120.0 MB = its algorithmic reads, L2 hit rate 0.04 % (profiles/r01_half_shard_probe.txt) -- so
+// the split changes the SCHEDULE of the NUM_RUNS x options evaluations, never what a run reads.
+int price_subshards(const bs_gpu_ctx *c, const Shard &s)
+{
+    const size_t bytes = s.count * (6 * (size_t)c->fp_bytes + 4);  // six fptype streams (5 in, 1 out) + otype
+    const size_t min_bytes = (size_t)128 << 20;
+    return (int)std::max<size_t>(1, std::min<size_t>(PIPE_CHUNKS, bytes / min_bytes));
+}
+
+// bs_gpu_price() on one device, sub-shard scheme (shards of >= 256 MiB): the shard is cut into S contiguous
+// sub-shards, each larger than the L2, and sub-shard i runs ALL its NUM_RUNS launches as soon as its inputs have
+// landed, while sub-shard i+1 is still on the PCIe bus and the prices of sub-shard i-1 travel back:
+//   H2D engine    : in 0 | in 1 | in 2 ...
+//   launch stream :        R runs on 0 | R runs on 1 | ...
+//   D2H engine    :                      out 0       | out 1 ...
+// Independent options make this legal: it is the time-multiplexed twin of sharding over several GPUs, where every
+// device also runs all NUM_RUNS over its own range without waiting for the others.
+void do_price_subshards(bs_gpu_ctx *c, Shard &s, int S)
+{
+    const int R = c->arg_num_runs;
+    const bool chk = c->arg_err_chk != 0;
+    const int what = c->arg_upload_what;
+    size_t lo[PIPE_CHUNKS + 1];
+    const size_t per = ((s.count + S - 1) / S + 1023) & ~(size_t)1023;
+    for (int k = 0; k <= S; k++) lo[k] = std::min(s.count, per * (size_t)k);
+    lo[S] = s.count;
+    const size_t pe = elem_bytes(c, BS_BUF_PRICES);
+
+    // graphs first (instantiation must not sit between the timing marks)
+    cudaGraphExec_t exec[PIPE_CHUNKS];
+    for (int k = 0; k < S; k++) exec[k] = runs_graph(c, s, R, chk, true, lo[k], lo[k + 1] - lo[k]);
+
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev0, 0));
+    SH_CUDA(cudaStreamWaitEvent(s.d2h_stream, s.ev0, 0));
+    if (chk) reset_err_counters(s);
+    if (what) {
+        for (int k = 0; k < S; k++) {
+            const size_t n = lo[k + 1] - lo[k];
+            if (what & UP_INPUTS)
+                for (int b = BS_BUF_SPTPRICE; b <= BS_BUF_OTYPE; b++) {
+                    const size_t eb = elem_bytes(c, b);
+                    SH_CUDA(cudaMemcpyAsync((char *)s.d[b] + lo[k] * eb, (const char *)c->host[b] + (s.first + lo[k]) * eb, n * eb,
+                                            cudaMemcpyHostToDevice, s.copy_stream));
+                }
+            if ((what & UP_REFVAL) && s.d[BS_BUF_DGREFVAL]) {
+                const size_t eb = elem_bytes(c, BS_BUF_DGREFVAL);
+                SH_CUDA(cudaMemcpyAsync((char *)s.d[BS_BUF_DGREFVAL] + lo[k] * eb, (const char *)c->host[BS_BUF_DGREFVAL] + (s.first + lo[k]) * eb,
+                                        n * eb, cudaMemcpyHostToDevice, s.copy_stream));
+            }
+            SH_CUDA(cudaEventRecord(s.ev_in[k], s.copy_stream));
+        }
+        if ((what & UP_REFVAL) && s.d[BS_BUF_DGREFVAL]) s.refval_on_device = true;
+    }
+    SH_CUDA(cudaEventRecord(s.ev_h2d, s.copy_stream));
+    for (int k = 0; k < S; k++) {
+        if (what) SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_in[k], 0));
+        if (k == 0) SH_CUDA(cudaEventRecord(s.ev_k0, s.stream));
+        if (exec[k]) SH_CUDA(cudaGraphLaunch(exec[k], s.stream));
+        else enqueue_runs(c, s, R, chk, true, lo[k], lo[k + 1] - lo[k]);
+        SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
+    }
+    SH_CUDA(cudaGetLastError());
+    SH_CUDA(cudaEventRecord(s.ev_k1, s.stream));
+    for (int k = 0; k < S; k++) {
+        const size_t n = lo[k + 1] - lo[k];
+        SH_CUDA(cudaStreamWaitEvent(s.d2h_stream, s.ev_out[k], 0));
+        if (n)
+            SH_CUDA(cudaMemcpyAsync((char *)c->host[BS_BUF_PRICES] + (s.first + lo[k]) * pe, (const char *)s.d[BS_BUF_PRICES] + lo[k] * pe, n * pe,
+                                    cudaMemcpyDeviceToHost, s.d2h_stream));
+    }
+    SH_CUDA(cudaEventRecord(s.ev1, s.d2h_stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaStreamSynchronize(s.stream));
+    SH_CUDA(cudaStreamSynchronize(s.copy_stream));
+    SH_CUDA(cudaEventElapsedTime(&s.pipeline_ms, s.ev0, s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.h2d_ms, s.ev0, s.ev_h2d));
+    SH_CUDA(cudaEventElapsedTime(&s.roi_ms, s.ev_k0, s.ev_k1));
+    SH_CUDA(cudaEventElapsedTime(&s.d2h_ms, s.ev_k1, s.ev1));
+    fetch_err_results(c, s, chk);
+}
+
 void do_price(bs_gpu_ctx *c, Shard &s)
 {
     const int R = c->arg_num_runs;
@@ -453,6 +548,10 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     s.h2d_ms = s.roi_ms = s.d2h_ms = s.pipeline_ms = 0;
     ensure_pinned(c, s);
     if (s.count == 0) { s.err_total = 0; s.list_n = 0; s.list.clear(); return; }
+    {
+        const int S = price_subshards(c, s);
+        if (S > 1 && R >= 1 && !(c->flags & BS_GPU_FLAG_NO_SUBSHARDS)) { do_price_subshards(c, s, S); return; }
+    }
 
     // chunk boundaries: multiples of 1024 options keep every stream 16-byte aligned
     size_t lo[PIPE_CHUNKS + 1];
@@ -612,6 +711,7 @@ void do_teardown(bs_gpu_ctx *c, Shard &s)
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
     if (s.copy_stream) cudaStreamSynchronize(s.copy_stream);
+    if (s.d2h_stream) cudaStreamSynchronize(s.d2h_stream);
     unpin(c, s);
     for (auto &kv : s.graphs) cudaGraphExecDestroy(kv.second);
     s.graphs.clear();
@@ -627,8 +727,9 @@ void do_teardown(bs_gpu_ctx *c, Shard &s)
         if (s.ev_out[i]) cudaEventDestroy(s.ev_out[i]);
     }
     if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+    if (s.d2h_stream) cudaStreamDestroy(s.d2h_stream);
     if (s.stream) cudaStreamDestroy(s.stream);
-    s.copy_stream = nullptr;
+    s.copy_stream = s.d2h_stream = nullptr;
     s.d_table = nullptr; s.d_list = nullptr; s.d_list_count = nullptr; s.d_err_count = nullptr;
     s.arena = nullptr; s.ev0 = s.ev1 = nullptr; s.stream = nullptr;
 }

@@ -23,7 +23,7 @@ BUF_NAMES = ("sptprice", "strike", "rate", "volatility", "otime", "otype", "pric
 # enum bs_gpu_math
 MATH_DEFAULT, MATH_IEEE, MATH_FAST = 0, 1, 2
 # flags
-FLAG_NO_HOST_STAGING, FLAG_WITH_DGREFVAL, FLAG_NO_GRAPH, FLAG_ASYNC_DISCOVERY, FLAG_PDL = 1, 2, 4, 8, 16
+FLAG_NO_HOST_STAGING, FLAG_WITH_DGREFVAL, FLAG_NO_GRAPH, FLAG_ASYNC_DISCOVERY, FLAG_PDL, FLAG_NO_SUBSHARDS = 1, 2, 4, 8, 16, 32
 
 NUM_RUNS = 100  # blackscholes.c:87
 
@@ -128,7 +128,7 @@ class BlackScholesGPU:
     """One bs_gpu_ctx.  `devices` is a list of CUDA ordinals (one contiguous shard each)."""
 
     def __init__(self, num_options, fp_bytes=4, devices=None, num_gpus=None, math=MATH_DEFAULT, host_staging=True,
-                 with_dgrefval=True, use_graph=True, threads_per_block=0, blocks_per_sm=0, unroll=0, variant=0, async_discovery=False, pdl=False):
+                 with_dgrefval=True, use_graph=True, threads_per_block=0, blocks_per_sm=0, unroll=0, variant=0, async_discovery=False, pdl=False, subshards=True):
         self._L = load_library()
         self._ctx = ctypes.c_void_p()
         if devices is None:
@@ -146,7 +146,7 @@ class BlackScholesGPU:
         cfg.num_gpus = len(self.devices)
         cfg.devices = dev_arr
         cfg.flags = (0 if host_staging else FLAG_NO_HOST_STAGING) | (FLAG_WITH_DGREFVAL if with_dgrefval else 0) | \
-                    (0 if use_graph else FLAG_NO_GRAPH) | (FLAG_ASYNC_DISCOVERY if async_discovery else 0) | (FLAG_PDL if pdl else 0)
+                    (0 if use_graph else FLAG_NO_GRAPH) | (FLAG_ASYNC_DISCOVERY if async_discovery else 0) | (FLAG_PDL if pdl else 0) | (0 if subshards else FLAG_NO_SUBSHARDS)
         cfg.math = math
         cfg.threads_per_block = threads_per_block
         cfg.blocks_per_sm = blocks_per_sm

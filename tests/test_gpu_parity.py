@@ -265,6 +265,33 @@ def test_maximum_option_count_int32():
             host.BlackScholesGPU(2**31)                            # one more does not fit an int: rejected
 
 
+def test_subshard_pipeline_equals_run_order():
+    # shards above 256 MiB are priced sub-shard by sub-shard inside bs_gpu_price (copies hidden behind the runs of
+    # the neighbouring sub-shard); the prices, the ERR_CHK count and the offender list must not depend on it
+    n = 10_000_003                                        # 2 sub-shards, ragged tail in the second
+    s, k, r, v, t, o = inputgen_like(n, seed=5)
+    ref = oracle_lib.price_map(s[:4096], k[:4096], r[:4096], v[:4096], t[:4096], o[:4096], 4)
+    bad_rows = np.array([0, 1, 4_999_999, 5_000_000, 5_000_319, 7_777_777, n - 2, n - 1])
+    results = []
+    for sub in (True, False):
+        with host.BlackScholesGPU(n, subshards=sub) as bs:
+            bs.set_inputs(s, k, r, v, t, o)
+            bs.price(1)
+            dg = bs.prices.copy()
+            dg[bad_rows] += 1.0
+            bs.host("dgrefval")[:] = dg
+            bs.mark_dirty()
+            errs = bs.price(3, err_chk=True)
+            tm = bs.timing()
+            assert tm["h2d_bytes"] == n * 28 and tm["d2h_bytes"] == n * 4 and tm["kernel_launches"] == 3
+            results.append((bs.prices.copy(), errs, bs.errors().tolist(), tm["pipeline_ms"]))
+    assert results[0][0].tobytes() == results[1][0].tobytes()
+    assert results[0][1] == results[1][1] == 3 * len(bad_rows)
+    assert results[0][2] == results[1][2] == bad_rows.tolist()
+    assert np.abs(results[0][0][:4096] - ref).max() <= FP32_ABS_TOL
+    print("bs_gpu_price 10M options x 3 runs: %.2f ms with sub-shards, %.2f ms in run order" % (results[0][3], results[1][3]))
+
+
 def test_scaling_homogeneity():
     # price(2s, 2k) == 2 price(s, k): doubling is exact in binary floating point
     inputs = list(inputgen_like(100000, seed=12))
