@@ -113,3 +113,34 @@ def test_product_never_touches_the_oracle():
 def test_bytes_per_option():
     assert host.bytes_per_option(4) == 28 and host.bytes_per_option(8) == 52
     assert host.bytes_per_option(4, err_chk=True) == 32
+
+
+C_PROBE = r"""
+#include <stdio.h>
+#include "bs_gpu.h"
+#include "bs_io.h"
+int main(void)
+{
+    bs_gpu_config cfg = {0};
+    bs_gpu_ctx *ctx = NULL;
+    bs_gpu_timing tm;
+    (void)tm;
+    cfg.struct_size = sizeof(cfg);
+    cfg.num_options = 16; cfg.fp_bytes = 3; cfg.num_gpus = 1;     /* invalid fptype: rejected before any device */
+    printf("%d %d %s %d\n", bs_gpu_abi_version(), bs_gpu_init_ex(&ctx, &cfg), bs_gpu_status_string(BS_GPU_ERR_NO_DEVICE),
+           (int)BS_BUF_COUNT);
+    return ctx != NULL;
+}
+"""
+
+
+def test_headers_are_plain_c_and_link(tmp_path):
+    # the boundary is a C ABI: both headers must compile as C99 with -pedantic and link against the library
+    src = tmp_path / "probe.c"
+    src.write_text(C_PROBE)
+    exe = str(tmp_path / "probe")
+    lib_dir = os.path.dirname(host.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                    "-L", lib_dir, "-lbs_gpu", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["1", "-1", "no", "usable", "CUDA", "device", "8"]

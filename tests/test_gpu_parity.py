@@ -419,3 +419,14 @@ def test_driver_soa_cache(tmp_path):
     out = str(tmp_path / "p2.txt")
     cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu_errchk"), "1", inp + ".bssoa", out], capture_output=True, text=True)
     assert cp.returncode == 0 and "binary SoA file" in cp.stdout and "Num Errors: 0" in cp.stdout and open(out).read() == outs[0]
+
+
+@pytest.mark.skipif(oracle_lib.ref_binary("blackscholes_gpu_hooks") is None, reason="oracle/_ref/blackscholes_gpu_hooks not built")
+def test_driver_with_parsec_hooks(tmp_path):
+    # -DENABLE_PARSEC_HOOKS build of the drop-in driver (against the hooks shim): the ROI lines come from the hooks
+    out = str(tmp_path / "p.txt")
+    stdout, roi = oracle_lib.run_ref("blackscholes_gpu_hooks", 1, golden_path("table1k", "in.txt"), out)
+    lines = stdout.splitlines()
+    assert roi is not None and "[HOOKS] shim (oracle/hooks_shim/hooks.h)" in lines
+    assert lines.index("[HOOKS] Entering ROI") < lines.index("[HOOKS] Leaving ROI") < lines.index("[HOOKS] Terminating")
+    assert_parity(np.loadtxt(out, skiprows=1), _golden_prices("table1k", "f32"), 4, "hooks build")
