@@ -100,7 +100,8 @@ typedef struct bs_gpu_config {
     int blocks_per_sm;     /* 0 = default (all the CTAs the SM can hold)                             */
     int unroll;            /* 0 = default; else 1, 2 or 4 independent 16-byte groups per thread-trip */
     int variant;           /* 0 = default; bit 0: software-pipelined loads; bit 1: DIAGNOSTIC traffic probe
-                              (no pricing, same streams) -- see DESIGN.md                                */
+                              (no pricing, same streams); bit 2: TMA variant (inputs moved by cp.async.bulk
+                              into a shared-memory ring) -- see DESIGN.md                                */
 } bs_gpu_config;
 
 typedef struct bs_gpu_timing {

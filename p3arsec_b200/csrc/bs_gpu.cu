@@ -78,6 +78,7 @@ struct Shard {
     float pipeline_ms = 0;
     std::map<GraphKey, cudaGraphExec_t> graphs;
     int threads = 0, blocks = 0;
+    int tma_blocks = 0;  // grid of the TMA variant: SMs x CTAs that fit (one or two, 150 KB of shared memory each)
     // results of the last command
     int status = BS_GPU_OK;
     std::string err;
@@ -157,8 +158,10 @@ typedef void (*KernelF64)(bsk::StreamsF64, size_t, bsk::ErrChk);
 // bs_gpu_config.variant bits
 enum {
     VARIANT_PIPE = 1,   // software-pipelined loads (next trip in flight during the math)
-    VARIANT_PROBE = 2   // DIAGNOSTIC ONLY: no pricing, same seven streams (sum of the inputs is written): the
+    VARIANT_PROBE = 2,  // DIAGNOSTIC ONLY: no pricing, same seven streams (sum of the inputs is written): the
                         // bandwidth ceiling of this traffic pattern.  Never selected by default.
+    VARIANT_TMA = 4     // inputs moved by cp.async.bulk into a shared-memory ring (bs_map_tma); ERR_CHK runs use
+                        // the plain kernel
 };
 
 template <typename FP, int MATH, bool CHK, bool PIPE>
@@ -182,6 +185,15 @@ void (*pick_kernel(int math, int unroll, bool chk, bool pipe))(bsk::Streams<FP>,
     return pipe ? pick_unroll<FP, bsk::MATH_FAST, false, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, false, false>(unroll);
 }
 int kernel_math(const bs_gpu_ctx *c) { return (c->variant & VARIANT_PROBE) ? (int)bsk::MATH_PROBE : c->math; }
+bool use_tma(const bs_gpu_ctx *c, bool chk) { return (c->variant & VARIANT_TMA) && !chk; }
+template <typename FP> const void *tma_kernel(int math)
+{
+    if (math == bsk::MATH_PROBE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_PROBE>;
+    if (math == BS_MATH_IEEE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_IEEE>;
+    return (const void *)bsk::bs_map_tma<FP, bsk::MATH_FAST>;
+}
+const void *tma_kernel_ptr(const bs_gpu_ctx *c) { return c->fp_bytes == 4 ? tma_kernel<float>(kernel_math(c)) : tma_kernel<double>(kernel_math(c)); }
+size_t tma_smem(const bs_gpu_ctx *c) { return c->fp_bytes == 4 ? bsk::tma_smem_bytes<float>() : bsk::tma_smem_bytes<double>(); }
 KernelF32 pick_f32(const bs_gpu_ctx *c, bool chk) { return pick_kernel<float>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 KernelF64 pick_f64(const bs_gpu_ctx *c, bool chk) { return pick_kernel<double>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
@@ -193,13 +205,14 @@ const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
 // programmatic-stream-serialization attribute: behind another Map launch it may begin (and issue its first loads)
 // while that one drains; the kernel itself orders its stores after the predecessor (griddepcontrol.wait).  Behind
 // a copy or memset the attribute has no effect.  Captured into the runs graph as a programmatic edge.
-void launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *streams, size_t *count, bsk::ErrChk *ec, bool allow_pdl)
+void launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *streams, size_t *count, bsk::ErrChk *ec, bool allow_pdl,
+                   int threads = 0, size_t smem = 0)
 {
     void *args[3] = {streams, count, ec};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3((unsigned)s.threads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.blockDim = dim3((unsigned)(threads ? threads : s.threads));
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -237,7 +250,8 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (float *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const float *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        launch_kernel(c, s, (const void *)pick_f32(c, chk), blocks, &a, &count, &ec, allow_pdl);
+        if (use_tma(c, chk)) launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
+        else launch_kernel(c, s, (const void *)pick_f32(c, chk), blocks, &a, &count, &ec, allow_pdl);
     } else {
         bsk::StreamsF64 a;
         a.spt = (const double *)s.d[BS_BUF_SPTPRICE] + first;
@@ -248,7 +262,8 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (double *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        launch_kernel(c, s, (const void *)pick_f64(c, chk), blocks, &a, &count, &ec, allow_pdl);
+        if (use_tma(c, chk)) launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
+        else launch_kernel(c, s, (const void *)pick_f64(c, chk), blocks, &a, &count, &ec, allow_pdl);
     }
 }
 
@@ -347,6 +362,14 @@ void do_setup(bs_gpu_ctx *c, Shard &s)
     if (blocks < 1) blocks = 1;
     s.threads = threads;
     s.blocks = (int)blocks;
+    if (c->variant & VARIANT_TMA) {
+        SH_CUDA(cudaFuncSetAttribute(tma_kernel_ptr(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem(c)));
+        int fit = 0;
+        SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, tma_kernel_ptr(c), bsk::TMA_THREADS, tma_smem(c)));
+        if (fit < 1) fit = 1;
+        if (c->cfg_blocks_per_sm > 0) fit = std::min(fit, c->cfg_blocks_per_sm);
+        s.tma_blocks = s.sm_count * fit;
+    }
     SH_CUDA(cudaStreamSynchronize(s.stream));
 }
 
@@ -922,7 +945,7 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (cfg->threads_per_block != 0 && (cfg->threads_per_block < 32 || cfg->threads_per_block > 256 || cfg->threads_per_block % 32))
         return BS_GPU_ERR_INVALID;
     if (cfg->blocks_per_sm < 0 || cfg->blocks_per_sm > 32) return BS_GPU_ERR_INVALID;
-    if (cfg->variant < 0 || cfg->variant > 3) return BS_GPU_ERR_INVALID;
+    if (cfg->variant < 0 || cfg->variant > 7) return BS_GPU_ERR_INVALID;
     if ((cfg->variant & VARIANT_PIPE) && cfg->unroll == 4) return BS_GPU_ERR_INVALID;  // would spill: not built for use
     if (cfg->num_options > 2147483647ull) return BS_GPU_ERR_INVALID;  // the reference's `int numOptions`
 

@@ -425,6 +425,136 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA variant (bs_gpu_config.variant bit 2): the same Map with the input streams moved by the bulk-copy engine.
+//   * one persistent CTA per SM slot; warp 8 is the PRODUCER: one elected lane issues, per tile, six
+//     cp.async.bulk global->shared copies (one per input stream, TILE options each) that complete on the stage's
+//     "full" mbarrier (expect_tx = bytes of the tile);
+//   * warps 0-7 are CONSUMERS: wait on "full", LDS.128 their group out of every stream tile, release the stage
+//     ("empty" mbarrier, one arrival per warp) BEFORE doing the math, price, STG.128 the prices;
+//   * STAGES tiles are in flight per CTA (STAGES x 24 KB fp32), so no registers are tied up by loads in flight and
+//     the LSU issues six LDS instead of six LDG + their 64-bit address arithmetic per group.
+// Whole tiles only; the last n % TILE options are priced by the consumers of block 0 with plain loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename FP> struct TmaCfg;
+template <> struct TmaCfg<float> { enum { TILE = 1024, STAGES = 4 }; };   // 6 x 4 KB per stage; 96 KB per CTA, 2 CTAs per SM
+template <> struct TmaCfg<double> { enum { TILE = 512, STAGES = 4 }; };   // 5 x 4 KB + 2 KB per stage; 88 KB per CTA
+enum { TMA_CONSUMERS = 256, TMA_THREADS = TMA_CONSUMERS + 32 };
+
+template <typename FP> __host__ __device__ constexpr size_t tma_stage_bytes() { return (size_t)TmaCfg<FP>::TILE * (5 * sizeof(FP) + sizeof(int)); }
+template <typename FP> __host__ __device__ constexpr size_t tma_smem_bytes()
+{
+    return tma_stage_bytes<FP>() * TmaCfg<FP>::STAGES + 2 * TmaCfg<FP>::STAGES * sizeof(uint64_t) + 128 +
+           ((sizeof(FP) == 8) ? bsm::TAB_DOUBLES * sizeof(double) : 0);
+}
+
+template <typename FP, int MATH>
+__global__ void __launch_bounds__(TMA_THREADS, 2) bs_map_tma(Streams<FP> a, size_t n, ErrChk ec)
+{
+    typedef typename VT<FP>::vec vec;
+    typedef typename VT<FP>::ivec ivec;
+    enum { LANES = VT<FP>::LANES, TILE = TmaCfg<FP>::TILE, STAGES = TmaCfg<FP>::STAGES, GROUPS = TILE / LANES };
+    constexpr unsigned FP_TILE_BYTES = TILE * sizeof(FP), OT_TILE_BYTES = TILE * sizeof(int);
+    constexpr unsigned STAGE_BYTES = 5 * FP_TILE_BYTES + OT_TILE_BYTES;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *stage_base = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGE_BYTES * STAGES);
+    uint64_t *empty = full + STAGES;
+    double *s_tab = reinterpret_cast<double *>(empty + STAGES + 2);
+    enum { USE_TAB = (sizeof(FP) == 8 && MATH == MATH_FAST) ? 1 : 0 };
+    (void)ec;
+
+    const size_t tiles = n / TILE;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < STAGES; st++) {
+            mbar_init(&full[st], 1);                      // the producer's expect_tx arrival
+            mbar_init(&empty[st], TMA_CONSUMERS / 32);    // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (USE_TAB) bsm::fill_tables(s_tab, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+
+    if (warp == TMA_CONSUMERS / 32) {
+        // ---- producer: one lane keeps STAGES tiles in flight
+        if ((threadIdx.x & 31) == 0) {
+            unsigned it = 0;
+            for (size_t t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
+                const int st = it % STAGES;
+                const unsigned round = it / STAGES;
+                if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);   // consumers have drained this stage
+                unsigned char *dst = stage_base + (size_t)st * STAGE_BYTES;
+                const size_t o0 = t * TILE;
+                mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+                bulk_g2s(dst + 0 * FP_TILE_BYTES, a.spt + o0, FP_TILE_BYTES, &full[st]);
+                bulk_g2s(dst + 1 * FP_TILE_BYTES, a.strike + o0, FP_TILE_BYTES, &full[st]);
+                bulk_g2s(dst + 2 * FP_TILE_BYTES, a.rate + o0, FP_TILE_BYTES, &full[st]);
+                bulk_g2s(dst + 3 * FP_TILE_BYTES, a.vol + o0, FP_TILE_BYTES, &full[st]);
+                bulk_g2s(dst + 4 * FP_TILE_BYTES, a.otime + o0, FP_TILE_BYTES, &full[st]);
+                bulk_g2s(dst + 5 * FP_TILE_BYTES, a.otype + o0, OT_TILE_BYTES, &full[st]);
+            }
+        }
+    } else {
+        // ---- consumers
+        vec *p_out = reinterpret_cast<vec *>(a.prices);
+        unsigned it = 0;
+        for (size_t t = blockIdx.x; t < tiles; t += gridDim.x, it++) {
+            const int st = it % STAGES;
+            mbar_wait(&full[st], (it / STAGES) & 1);
+            const unsigned char *src = stage_base + (size_t)st * STAGE_BYTES;
+            // GROUPS groups per tile, 256 consumers: fp32 exactly one group each (1024/4), fp64 too (512/2)
+            static_assert(GROUPS == TMA_CONSUMERS, "one group per consumer thread and tile");
+            const int gi = threadIdx.x;
+            const vec vs = reinterpret_cast<const vec *>(src + 0 * FP_TILE_BYTES)[gi];
+            const vec vk = reinterpret_cast<const vec *>(src + 1 * FP_TILE_BYTES)[gi];
+            const vec vr = reinterpret_cast<const vec *>(src + 2 * FP_TILE_BYTES)[gi];
+            const vec vv = reinterpret_cast<const vec *>(src + 3 * FP_TILE_BYTES)[gi];
+            const vec vt = reinterpret_cast<const vec *>(src + 4 * FP_TILE_BYTES)[gi];
+            const ivec vo = reinterpret_cast<const ivec *>(src + 5 * FP_TILE_BYTES)[gi];
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);   // stage is free again: refill overlaps our math
+            vec p;
+#pragma unroll
+            for (int l = 0; l < LANES; l++)
+                set_lane(p, l, price_any<MATH>(lane(vs, l), lane(vk, l), lane(vr, l), lane(vv, l), lane(vt, l), lane(vo, l), s_tab));
+            st_stream(p_out + t * GROUPS + gi, p);
+        }
+        // the last n % TILE options (no whole tile): plain loads, block 0 only
+        if (blockIdx.x == 0) {
+            for (size_t i = tiles * TILE + threadIdx.x; i < n; i += TMA_CONSUMERS)
+                a.prices[i] = price_any<MATH>(a.spt[i], a.strike[i], a.rate[i], a.vol[i], a.otime[i], a.otype[i], s_tab);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Synthetic fill: option i of the shard = table[(first + i) % rows]   (inputgen's cyclic replay)
 // ---------------------------------------------------------------------------------------------
 template <typename FP>

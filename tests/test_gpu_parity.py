@@ -109,9 +109,19 @@ def test_launch_geometry_does_not_change_results(fp_bytes):
     base, _, _ = gpu_prices(inputs, fp_bytes)
     for kw in (dict(unroll=1), dict(unroll=2), dict(unroll=4), dict(threads_per_block=128), dict(threads_per_block=64, blocks_per_sm=3),
                dict(blocks_per_sm=1, unroll=1), dict(use_graph=False), dict(pdl=True), dict(pdl=True, use_graph=False), dict(pdl=True, unroll=2), dict(variant=1), dict(variant=1, unroll=2, threads_per_block=128),
-               dict(variant=1, unroll=1, blocks_per_sm=1, threads_per_block=32)):
+               dict(variant=1, unroll=1, blocks_per_sm=1, threads_per_block=32), dict(variant=4), dict(variant=4, blocks_per_sm=1)):
         got, _, _ = gpu_prices(inputs, fp_bytes, **kw)
         assert got.tobytes() == base.tobytes(), kw
+
+
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+@pytest.mark.parametrize("n", [1, 1023, 1024, 1025, 4096, 300007, 5_000_123])
+def test_tma_variant_sizes(n, fp_bytes):
+    # bulk-copy (TMA) variant: whole tiles through the shared-memory ring, the remainder by plain loads
+    inputs = inputgen_like(n, seed=n + 1, dtype=np.float32 if fp_bytes == 4 else np.float64)
+    base, _, _ = gpu_prices(inputs, fp_bytes, num_runs=2)
+    got, _, _ = gpu_prices(inputs, fp_bytes, num_runs=2, variant=4)
+    assert got.tobytes() == base.tobytes()
 
 
 def test_num_runs_is_idempotent_and_counts_launches():
