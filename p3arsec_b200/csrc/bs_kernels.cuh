@@ -463,9 +463,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 template <typename FP> struct TmaCfg;
-template <> struct TmaCfg<float> { enum { TILE = 1024, STAGES = 4 }; };   // 6 x 4 KB per stage; 96 KB per CTA, 2 CTAs per SM
-template <> struct TmaCfg<double> { enum { TILE = 512, STAGES = 4 }; };   // 5 x 4 KB + 2 KB per stage; 88 KB per CTA
-enum { TMA_CONSUMERS = 256, TMA_THREADS = TMA_CONSUMERS + 32 };
+template <> struct TmaCfg<float> { enum { TILE = 2048, STAGES = 4 }; };   // 6 x 8 KB per stage; 192 KB per CTA, 1 CTA per SM
+template <> struct TmaCfg<double> { enum { TILE = 1024, STAGES = 4 }; };  // 5 x 8 KB + 4 KB per stage; 176 KB per CTA
+enum { TMA_CONSUMERS = 512, TMA_THREADS = TMA_CONSUMERS + 32 };
 
 template <typename FP> __host__ __device__ constexpr size_t tma_stage_bytes() { return (size_t)TmaCfg<FP>::TILE * (5 * sizeof(FP) + sizeof(int)); }
 template <typename FP> __host__ __device__ constexpr size_t tma_smem_bytes()
@@ -475,7 +475,7 @@ template <typename FP> __host__ __device__ constexpr size_t tma_smem_bytes()
 }
 
 template <typename FP, int MATH>
-__global__ void __launch_bounds__(TMA_THREADS, 2) bs_map_tma(Streams<FP> a, size_t n, ErrChk ec)
+__global__ void __launch_bounds__(TMA_THREADS, 1) bs_map_tma(Streams<FP> a, size_t n, ErrChk ec)
 {
     typedef typename VT<FP>::vec vec;
     typedef typename VT<FP>::ivec ivec;
