@@ -253,10 +253,12 @@ def test_native_10m_put_call_parity_and_bounds():
     assert np.abs((call - put) - fwd).max() <= 1e-4        # C - P = S - K e^{-rT}
     assert (call >= np.maximum(fwd, 0) - 1e-4).all() and (call <= s64 + 1e-4).all()
     assert (put >= np.maximum(-fwd, 0) - 1e-4).all() and (put <= k64 + 1e-4).all()
-    # spot check 100k random rows against the oracle
-    idx = np.random.RandomState(1).choice(n, 100000, replace=False)
-    ref = oracle_lib.price_map(s[idx], k[idx], r[idx], v[idx], t[idx], np.zeros(len(idx), np.int32), 4)
-    assert np.abs(call[idx] - ref).max() <= FP32_ABS_TOL
+    # and every one of the 10M calls and puts against the oracle (all host cores: well under a second)
+    ref_c = oracle_lib.price_map(s, k, r, v, t, np.zeros(n, np.int32), 4).astype(np.float64)
+    ref_p = oracle_lib.price_map(s, k, r, v, t, np.ones(n, np.int32), 4).astype(np.float64)
+    worst = max(np.abs(call - ref_c).max(), np.abs(put - ref_p).max())
+    print("fp32 fast, 2 x 10M random inputgen-range options: max|delta| vs oracle = %.3e" % worst)
+    assert worst <= FP32_ABS_TOL
 
 
 def test_maximum_option_count_int32():
@@ -300,6 +302,18 @@ def test_subshard_pipeline_equals_run_order():
     assert results[0][2] == results[1][2] == bad_rows.tolist()
     assert np.abs(results[0][0][:4096] - ref).max() <= FP32_ABS_TOL
     print("bs_gpu_price 10M options x 3 runs: %.2f ms with sub-shards, %.2f ms in run order" % (results[0][3], results[1][3]))
+
+
+@pytest.mark.parametrize("fp_bytes,math,mname", [(4, host.MATH_IEEE, "ieee"), (8, host.MATH_FAST, "fast"), (8, host.MATH_IEEE, "ieee")])
+def test_native_10m_every_option_against_oracle(fp_bytes, math, mname):
+    n = 10_000_000
+    dt = np.float32 if fp_bytes == 4 else np.float64
+    inputs = inputgen_like(n, seed=78, dtype=dt)
+    got, _, _ = gpu_prices(inputs, fp_bytes, num_runs=1, math=math, with_dgrefval=False)
+    ref = oracle_prices(inputs, fp_bytes)
+    worst = assert_parity(got, ref, fp_bytes, "10M/%s" % mname)
+    print("fp%d %s, 10M random inputgen-range options: max|delta| vs oracle = %.3e, bit-identical %.1f%%" % (
+        8 * fp_bytes, mname, worst, 100.0 * float(np.mean(got == ref))))
 
 
 def test_scaling_homogeneity():
