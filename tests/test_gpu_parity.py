@@ -454,3 +454,21 @@ def test_driver_with_parsec_hooks(tmp_path):
     assert roi is not None and "[HOOKS] shim (oracle/hooks_shim/hooks.h)" in lines
     assert lines.index("[HOOKS] Entering ROI") < lines.index("[HOOKS] Leaving ROI") < lines.index("[HOOKS] Terminating")
     assert_parity(np.loadtxt(out, skiprows=1), _golden_prices("table1k", "f32"), 4, "hooks build")
+
+
+def test_rt0_degenerate_fp32_fast_follows_reference():
+    # t = 0 / v = 0 in fp32: the fast path must give what the reference gives (intrinsic value or NaN), via the
+    # -inf clamp of ex2_accurate and MUFU's IEEE specials
+    s = np.array([100.0, 90.0, 100.0, 100.0, 100.0], np.float32)
+    k = np.array([90.0, 100.0, 100.0, 90.0, 110.0], np.float32)
+    r = np.full(5, 0.05, np.float32)
+    v = np.array([0.2, 0.2, 0.2, 0.0, 0.0], np.float32)
+    t = np.array([0.0, 0.0, 0.0, 1.0, 1.0], np.float32)
+    for o in (0, 1):
+        inputs = (s, k, r, v, t, np.full(5, o, np.int32))
+        ref = oracle_prices(inputs, 4)
+        for math in (host.MATH_IEEE, host.MATH_FAST):
+            got, _, _ = gpu_prices(inputs, 4, math=math)
+            assert (np.isnan(got) == np.isnan(ref)).all(), (o, math, got, ref)
+            m = ~np.isnan(ref)
+            assert np.allclose(got[m], ref[m], rtol=0, atol=1e-4), (o, math, got, ref)
