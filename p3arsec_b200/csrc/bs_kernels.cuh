@@ -19,9 +19,7 @@
  *   BS_MATH_IEEE  expf/logf/sqrtf and IEEE-rounded divisions in the reference's operation order
  *                 (pure fp32; the reference's double-literal promotions are not imitated).
  *   BS_MATH_FAST  9 MUFU ops per option (sqrt, rcp x3, lg2 x2, ex2 x3) with log2(e)/ln(2) and
- *                 1/sqrt(2 pi) folded into constants, Horner form of the degree-5 polynomial; the three
- *                 reciprocals get one Newton step and the three exponentials a polynomial fraction part
- *                 (ex2_accurate), because the raw MUFU errors were most of the distance to the reference.
+ *                 1/sqrt(2 pi) folded into constants, Horner form of the degree-5 polynomial.
  * fp64 always follows the reference's operation order with explicitly rounded (never contracted)
  * IEEE operations so that the only possible difference to the fp64 CPU build is the last ulp of
  * exp()/log().
@@ -85,34 +83,6 @@ __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ft
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// 2^x to ~1.2 ulp.  MUFU.EX2 alone is good to 2^-22 (4 ulp); that relative error lands, multiplied by the strike, in the
-// price (fv = k 2^(-r t log2 e)) and was the largest single contribution to the distance from the reference output.
-// Here: x = n + f, |f| <= 1/2; 2^f from a degree-6 polynomial (Chebyshev-interpolated, 7.1e-8 worst relative error
-// including the fp32 Horner evaluation), 2^n from MUFU.EX2 of an integer, which is exact (tests/test_gpu_parity.py).
-// Arguments below -150 give 0 (also for -inf, which the unclamped subtraction would turn into NaN).
-__device__ __forceinline__ float ex2_accurate(float x)
-{
-    x = fmaxf(x, -150.0f);
-    float n;
-    asm("cvt.rni.f32.f32 %0, %1;" : "=f"(n) : "f"(x));
-    const float f = x - n;
-    float q = 0.00015453163359779865f;
-    q = fmaf(q, f, 0.0013390863314270973f);
-    q = fmaf(q, f, 0.009618083015084267f);
-    q = fmaf(q, f, 0.055503569543361664f);
-    q = fmaf(q, f, 0.24022650718688965f);
-    q = fmaf(q, f, 0.6931471824645996f);
-    return fmaf(q, f, 1.0f) * mufu_ex2(n);
-}
-
-// 1/x to <= 1 ulp: MUFU.RCP plus one Newton step (the raw approximation's last-bit errors are amplified by the
-// degree-5 CNDF polynomial and by d1 = num / den).
-__device__ __forceinline__ float rcp_accurate(float x)
-{
-    const float r = mufu_rcp(x);
-    return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
-
 // ---------------------------------------------------------------------------------------------
 // fp32, BS_MATH_FAST
 // ---------------------------------------------------------------------------------------------
@@ -127,8 +97,8 @@ __device__ __forceinline__ float cndf_tail_fast(float d)
     const float A5 = 1.330274429f * 0.39894228040143270286f;
     const float NEG_HALF_LOG2E = -0.72134752044448170368f;
 
-    float k = rcp_accurate(fmaf(fabsf(d), 0.2316419f, 1.0f));
-    float e = ex2_accurate((d * NEG_HALF_LOG2E) * d);
+    float k = mufu_rcp(fmaf(fabsf(d), 0.2316419f, 1.0f));
+    float e = mufu_ex2((d * NEG_HALF_LOG2E) * d);
     float p = fmaf(k, A5, A4);
     p = fmaf(k, p, A3);
     p = fmaf(k, p, A2);
@@ -143,13 +113,13 @@ __device__ __forceinline__ float price_fast(float s, float k, float r, float v, 
 
     float sq = mufu_sqrt(t);                         // xSqrtTime            :224
     float den = v * sq;                              // xDen                 :238
-    float rden = rcp_accurate(den);
+    float rden = mufu_rcp(den);
     float lg = mufu_lg2(s) - mufu_lg2(k);            // log2(s/k)            :226
     float drift = fmaf(0.5f * v, v, r);              // r + v*v/2            :231-234
     float num = fmaf(lg, LN2, drift * t);            // (..)*t + ln(s/k)     :235-236
     float d1 = num * rden;                           //                      :239
     float d2 = d1 - den;                             //                      :240
-    float fv = k * ex2_accurate((r * NEG_LOG2E) * t);  // strike*exp(-r t)   :248
+    float fv = k * mufu_ex2((r * NEG_LOG2E) * t);    // strike*exp(-r t)     :248
 
     float w1 = cndf_tail_fast(d1);
     float w2 = cndf_tail_fast(d2);
