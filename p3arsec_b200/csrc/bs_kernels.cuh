@@ -12,17 +12,19 @@
  *   - persistent grid: blocks = SMs x resident CTAs/SM, interleaved grid-stride over 16-byte groups
  *     so that every SM owns the same number of groups (+-1) and no tail wave exists; UNROLL
  *     independent groups per thread per trip keep >= 96*UNROLL bytes in flight per thread.
- *   - no shared memory, no tensor cores (nothing is reused, nothing is a contraction).
+ *   - no tensor cores (nothing is a contraction); shared memory only for the fp64 lookup tables and, in the
+ *     alternative bs_map_tma kernel, for the bulk-copy ring.
  *   - the put/call select is branch-free; CNDF's sign handling uses N(-x) = 1 - N(x).
  *
- * Two fp32 math flavours (bs_gpu_math in include/bs_gpu.h):
- *   BS_MATH_IEEE  expf/logf/sqrtf and IEEE-rounded divisions in the reference's operation order
- *                 (pure fp32; the reference's double-literal promotions are not imitated).
- *   BS_MATH_FAST  9 MUFU ops per option (sqrt, rcp x3, lg2 x2, ex2 x3) with log2(e)/ln(2) and
- *                 1/sqrt(2 pi) folded into constants, Horner form of the degree-5 polynomial.
- * fp64 always follows the reference's operation order with explicitly rounded (never contracted)
- * IEEE operations so that the only possible difference to the fp64 CPU build is the last ulp of
- * exp()/log().
+ * Kernels: bs_map<FP, MATH, UNROLL, CHK, PIPE> (the default, LDG.128 streams; PIPE = software-pipelined loads),
+ * bs_map_tma<FP, MATH> (inputs by cp.async.bulk into a shared-memory ring; measured slower, kept as an option),
+ * bs_fill_synthetic<FP>.  Math flavours (bs_gpu_math in include/bs_gpu.h), both precisions:
+ *   BS_MATH_IEEE  libdevice exp/log/sqrt and IEEE-rounded divisions in the reference's operation order (fp32: pure
+ *                 fp32, the reference's double-literal promotions are not imitated; fp64: explicitly rounded, never
+ *                 contracted operations, so only the last ulp of exp()/log() can differ from the fp64 CPU build).
+ *   BS_MATH_FAST  fp32: 9 MUFU ops per option (sqrt, rcp x3, lg2 x2, ex2 x3) with log2(e)/ln(2) and 1/sqrt(2 pi)
+ *                 folded into constants, Horner form of the degree-5 polynomial.  fp64: bs_math_f64.h.
+ *   MATH_PROBE    diagnostic only: no pricing, same streams (the bandwidth ceiling of the traffic pattern).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -37,7 +39,6 @@ enum { MATH_PROBE = 0, MATH_IEEE = 1, MATH_FAST = 2 };  // MATH_PROBE: no pricin
 // ---------------------------------------------------------------------------------------------
 // 128-bit streaming accessors
 // ---------------------------------------------------------------------------------------------
-template <typename V> struct Vec16;  // 16-byte vector of T
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
 {
