@@ -101,7 +101,7 @@ typedef struct bs_gpu_config {
     int unroll;            /* 0 = default; else 1, 2 or 4 independent 16-byte groups per thread-trip */
     int variant;           /* 0 = default; bit 0: software-pipelined loads; bit 1: DIAGNOSTIC traffic probe
                               (no pricing, same streams); bit 2: TMA variant (inputs moved by cp.async.bulk
-                              into a shared-memory ring); bit 3: next trip prefetched into L2 -- see DESIGN.md */
+                              into a shared-memory ring) -- see DESIGN.md                                */
 } bs_gpu_config;
 
 typedef struct bs_gpu_timing {

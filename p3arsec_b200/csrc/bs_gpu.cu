@@ -160,33 +160,29 @@ enum {
     VARIANT_PIPE = 1,   // software-pipelined loads (next trip in flight during the math)
     VARIANT_PROBE = 2,  // DIAGNOSTIC ONLY: no pricing, same seven streams (sum of the inputs is written): the
                         // bandwidth ceiling of this traffic pattern.  Never selected by default.
-    VARIANT_TMA = 4,    // inputs moved by cp.async.bulk into a shared-memory ring (bs_map_tma); ERR_CHK runs use
+    VARIANT_TMA = 4     // inputs moved by cp.async.bulk into a shared-memory ring (bs_map_tma); ERR_CHK runs use
                         // the plain kernel
-    VARIANT_L2PREFETCH = 8  // the next trip is prefetched into L2 (no registers held), instead of VARIANT_PIPE
 };
 
-template <typename FP, int MATH, bool CHK, int PIPE>
+template <typename FP, int MATH, bool CHK, bool PIPE>
 void (*pick_unroll(int unroll))(bsk::Streams<FP>, size_t, bsk::ErrChk)
 {
     switch (unroll) {
     case 1: return bsk::bs_map<FP, MATH, 1, CHK, PIPE>;
-    case 4: return bsk::bs_map<FP, MATH, 4, CHK, PIPE == 1 ? 0 : PIPE>;  // register pipelining at UNROLL=4 would spill
+    case 4: return bsk::bs_map<FP, MATH, 4, CHK, PIPE>;
     default: return bsk::bs_map<FP, MATH, 2, CHK, PIPE>;
     }
 }
-template <typename FP, int MATH, bool CHK>
-void (*pick_pipe(int unroll, int pipe))(bsk::Streams<FP>, size_t, bsk::ErrChk)
-{
-    if (pipe == 1) return pick_unroll<FP, MATH, CHK, 1>(unroll);
-    if (pipe == 2) return pick_unroll<FP, MATH, CHK, 2>(unroll);
-    return pick_unroll<FP, MATH, CHK, 0>(unroll);
-}
 template <typename FP>
-void (*pick_kernel(int math, int unroll, bool chk, int pipe))(bsk::Streams<FP>, size_t, bsk::ErrChk)
+void (*pick_kernel(int math, int unroll, bool chk, bool pipe))(bsk::Streams<FP>, size_t, bsk::ErrChk)
 {
-    if (math == bsk::MATH_PROBE) return unroll == 1 ? bsk::bs_map<FP, bsk::MATH_PROBE, 1, false, 0> : bsk::bs_map<FP, bsk::MATH_PROBE, 2, false, 0>;
-    if (math == BS_MATH_IEEE) return chk ? pick_pipe<FP, bsk::MATH_IEEE, true>(unroll, pipe) : pick_pipe<FP, bsk::MATH_IEEE, false>(unroll, pipe);
-    return chk ? pick_pipe<FP, bsk::MATH_FAST, true>(unroll, pipe) : pick_pipe<FP, bsk::MATH_FAST, false>(unroll, pipe);
+    if (math == bsk::MATH_PROBE) return unroll == 1 ? bsk::bs_map<FP, bsk::MATH_PROBE, 1, false, false> : bsk::bs_map<FP, bsk::MATH_PROBE, 2, false, false>;
+    if (math == BS_MATH_IEEE) {
+        if (chk) return pipe ? pick_unroll<FP, bsk::MATH_IEEE, true, true>(unroll) : pick_unroll<FP, bsk::MATH_IEEE, true, false>(unroll);
+        return pipe ? pick_unroll<FP, bsk::MATH_IEEE, false, true>(unroll) : pick_unroll<FP, bsk::MATH_IEEE, false, false>(unroll);
+    }
+    if (chk) return pipe ? pick_unroll<FP, bsk::MATH_FAST, true, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, true, false>(unroll);
+    return pipe ? pick_unroll<FP, bsk::MATH_FAST, false, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, false, false>(unroll);
 }
 int kernel_math(const bs_gpu_ctx *c) { return (c->variant & VARIANT_PROBE) ? (int)bsk::MATH_PROBE : c->math; }
 bool use_tma(const bs_gpu_ctx *c, bool chk) { return (c->variant & VARIANT_TMA) && !chk; }
@@ -198,9 +194,8 @@ template <typename FP> const void *tma_kernel(int math)
 }
 const void *tma_kernel_ptr(const bs_gpu_ctx *c) { return c->fp_bytes == 4 ? tma_kernel<float>(kernel_math(c)) : tma_kernel<double>(kernel_math(c)); }
 size_t tma_smem(const bs_gpu_ctx *c) { return c->fp_bytes == 4 ? bsk::tma_smem_bytes<float>() : bsk::tma_smem_bytes<double>(); }
-int pipe_mode(const bs_gpu_ctx *c) { return (c->variant & VARIANT_PIPE) ? 1 : ((c->variant & VARIANT_L2PREFETCH) ? 2 : 0); }
-KernelF32 pick_f32(const bs_gpu_ctx *c, bool chk) { return pick_kernel<float>(kernel_math(c), c->unroll, chk, pipe_mode(c)); }
-KernelF64 pick_f64(const bs_gpu_ctx *c, bool chk) { return pick_kernel<double>(kernel_math(c), c->unroll, chk, pipe_mode(c)); }
+KernelF32 pick_f32(const bs_gpu_ctx *c, bool chk) { return pick_kernel<float>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
+KernelF64 pick_f64(const bs_gpu_ctx *c, bool chk) { return pick_kernel<double>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
 {
     return c->fp_bytes == 4 ? (const void *)pick_f32(c, chk) : (const void *)pick_f64(c, chk);
@@ -950,7 +945,7 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (cfg->threads_per_block != 0 && (cfg->threads_per_block < 32 || cfg->threads_per_block > 256 || cfg->threads_per_block % 32))
         return BS_GPU_ERR_INVALID;
     if (cfg->blocks_per_sm < 0 || cfg->blocks_per_sm > 32) return BS_GPU_ERR_INVALID;
-    if (cfg->variant < 0 || cfg->variant > 15) return BS_GPU_ERR_INVALID;
+    if (cfg->variant < 0 || cfg->variant > 7) return BS_GPU_ERR_INVALID;
     if ((cfg->variant & VARIANT_PIPE) && cfg->unroll == 4) return BS_GPU_ERR_INVALID;  // would spill: not built for use
     if (cfg->num_options > 2147483647ull) return BS_GPU_ERR_INVALID;  // the reference's `int numOptions`
 

@@ -310,7 +310,7 @@ struct Group {
 template <int MATH> __device__ __forceinline__ float price_any(float s, float k, float r, float v, float t, int o, const double *) { return price_f32<MATH>(s, k, r, v, t, o); }
 template <int MATH> __device__ __forceinline__ double price_any(double s, double k, double r, double v, double t, int o, const double *tab) { return price_f64_any<MATH>(s, k, r, v, t, o, tab); }
 
-template <typename FP, int MATH, int UNROLL, bool CHK, int PIPE>
+template <typename FP, int MATH, int UNROLL, bool CHK, bool PIPE>
 __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec)
 {
     typedef typename VT<FP>::vec vec;
@@ -381,30 +381,11 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
     // previous run's completion.  Our first trip of loads is issued before that wait, so the drain of run j and
     // the fill of run j+1 overlap instead of leaving the memory system idle between launches.  Every run still
     // reads every input and writes every price, in run order.  Both instructions are no-ops in a plain launch.
-    // PIPE == 2: the next trip is pulled into L2 by prefetch instructions (one lane per 128-byte line) while this
-    // trip is priced: no registers are held for it, the next trip's loads then cost an L2 hit instead of a DRAM access.
-    auto prefetch_trip = [&](size_t g0) {
-        if ((threadIdx.x & 7) == 0) {
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const size_t gi = g0 + u * stride;
-                if (gi < groups) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_s + gi));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_k + gi));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_r + gi));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_v + gi));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_t + gi));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_o + gi));
-                }
-            }
-        }
-    };
     asm volatile("griddepcontrol.launch_dependents;");
-    if (PIPE != 1) {
+    if (!PIPE) {
         if (g < groups) {
             Group<FP> cur[UNROLL];
             load_trip(cur, g);
-            if (PIPE == 2) prefetch_trip(g + (size_t)UNROLL * stride);
             asm volatile("griddepcontrol.wait;" ::: "memory");
             price_trip(cur, g);
             g += (size_t)UNROLL * stride;
@@ -414,7 +395,6 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
         for (; g < groups; g += (size_t)UNROLL * stride) {
             Group<FP> cur[UNROLL];
             load_trip(cur, g);
-            if (PIPE == 2) prefetch_trip(g + (size_t)UNROLL * stride);
             price_trip(cur, g);
         }
     } else if (g >= groups) {

@@ -109,7 +109,7 @@ def test_launch_geometry_does_not_change_results(fp_bytes):
     base, _, _ = gpu_prices(inputs, fp_bytes)
     for kw in (dict(unroll=1), dict(unroll=2), dict(unroll=4), dict(threads_per_block=128), dict(threads_per_block=64, blocks_per_sm=3),
                dict(blocks_per_sm=1, unroll=1), dict(use_graph=False), dict(pdl=True), dict(pdl=True, use_graph=False), dict(pdl=True, unroll=2), dict(variant=1), dict(variant=1, unroll=2, threads_per_block=128),
-               dict(variant=1, unroll=1, blocks_per_sm=1, threads_per_block=32), dict(variant=4), dict(variant=4, blocks_per_sm=1), dict(variant=8), dict(variant=8, unroll=2)):
+               dict(variant=1, unroll=1, blocks_per_sm=1, threads_per_block=32), dict(variant=4), dict(variant=4, blocks_per_sm=1)):
         got, _, _ = gpu_prices(inputs, fp_bytes, **kw)
         assert got.tobytes() == base.tobytes(), kw
 
