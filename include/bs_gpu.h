@@ -127,9 +127,9 @@ int bs_gpu_device_count(void);
  * ff's static partitioner does), allocates the device SoA arena + prices, and host staging for every
  * stream including DGREFVAL.  Replaces blackscholes.c:747-758 (+ :725).
  * Returns as soon as the staging buffers exist: the device contexts and arenas come up in the
- * background (so a loader can parse while CUDA initialises) and each device thread pins its page range
- * of the staging buffers before its first copy.  A device-side setup failure is reported by the first
- * later call that needs the devices. */
+ * background (so a loader can parse while CUDA initialises) and the device threads pin the staging
+ * buffers (cudaHostRegister) right before the first copy.  A device-side setup failure is reported by the
+ * first later call that needs the devices. */
 int bs_gpu_init(bs_gpu_ctx **ctx, int num_gpus, size_t num_options, int fp_bytes);
 
 /* Same, with explicit device list / flags / math mode / launch geometry. */

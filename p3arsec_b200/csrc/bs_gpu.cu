@@ -39,7 +39,7 @@
 
 namespace {
 
-enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_PRICE, CMD_FILL, CMD_TEARDOWN, CMD_EXIT };
+enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_PIN, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_PRICE, CMD_FILL, CMD_TEARDOWN, CMD_EXIT };
 
 enum { PIPE_CHUNKS = 8 };  // chunks of the first / last run of a pipelined bs_gpu_price()
 
@@ -87,7 +87,6 @@ struct Shard {
     unsigned int list_n = 0;
     std::vector<long long> list;
     bool refval_on_device = false;
-    bool host_pinned = false;  // this device thread's page range of every host stream is cudaHostRegister'ed
     std::thread worker;
 };
 
@@ -102,6 +101,8 @@ struct bs_gpu_ctx {
     std::vector<Shard> shards;
     void *host[BS_BUF_COUNT] = {nullptr};  // page-aligned anonymous mappings, pinned lazily by the device threads
     size_t host_bytes[BS_BUF_COUNT] = {0};
+    bool host_registered[BS_BUF_COUNT] = {false};  // written by the device thread that owns buffer b (b % G)
+    bool host_pinned = false;                      // CMD_PIN has run
     bool setup_pending = false;  // CMD_SETUP was posted by bs_gpu_init and has not been waited for yet
     int setup_status = BS_GPU_OK;
     // BS_GPU_FLAG_ASYNC_DISCOVERY: even device discovery (cuInit) runs in the background, on this thread
@@ -268,44 +269,34 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
 }
 
 
-// Page range of host stream b that device thread s pins: the pages are dealt out contiguously, without overlap,
-// at the page that contains the shard's first element (the last shard runs to the end of the mapping).
-void pin_range(const bs_gpu_ctx *c, const Shard &s, int b, size_t *lo, size_t *hi)
+// Pinning of the staging buffers (cudaHostRegister, portable).  Each buffer is registered WHOLE -- a copy whose host
+// range straddles two separate registrations is rejected by the runtime -- and the eight buffers are dealt out over
+// the device threads (buffer b goes to thread b % G) so the page pinning runs in parallel.  It happens once, as its
+// own broadcast command right before the first copy, i.e. after the loader has filled (and faulted in) the pages.
+// A failure is not fatal: copies from pageable memory still work, only slower.
+void do_pin(bs_gpu_ctx *c, Shard &s)
 {
-    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-    const size_t eb = elem_bytes(c, b);
-    *lo = s.first * eb / page * page;
-    const bool last = (size_t)s.index + 1 == c->shards.size();
-    *hi = last ? c->host_bytes[b] : (s.first + s.count) * eb / page * page;
-}
-
-// Pin this device's share of the staging buffers (idempotent).  A failure is not fatal: copies from pageable
-// memory still work, only slower, so the flag is simply left unset and the reason kept for bs_gpu_last_error().
-void ensure_pinned(bs_gpu_ctx *c, Shard &s)
-{
-    if (s.host_pinned || (c->flags & BS_GPU_FLAG_NO_HOST_STAGING)) return;
-    s.host_pinned = true;
-    for (int b = 0; b < BS_BUF_COUNT; b++) {
-        size_t lo, hi;
-        pin_range(c, s, b, &lo, &hi);
-        if (hi <= lo) continue;
-        const cudaError_t e = cudaHostRegister((char *)c->host[b] + lo, hi - lo, cudaHostRegisterPortable);
-        if (e != cudaSuccess) {
+    const int G = (int)c->shards.size();
+    for (int b = s.index; b < BS_BUF_COUNT; b += G) {
+        if (!c->host[b] || c->host_registered[b]) continue;
+        const cudaError_t e = cudaHostRegister(c->host[b], c->host_bytes[b], cudaHostRegisterPortable);
+        if (e == cudaSuccess) {
+            c->host_registered[b] = true;
+        } else {
             cudaGetLastError();
             s.err = std::string("cudaHostRegister: ") + cudaGetErrorString(e) + " (continuing with pageable copies)";
         }
     }
 }
 
-void unpin(bs_gpu_ctx *c, Shard &s)
+void do_unpin(bs_gpu_ctx *c, Shard &s)
 {
-    if (!s.host_pinned) return;
-    for (int b = 0; b < BS_BUF_COUNT; b++) {
-        size_t lo, hi;
-        pin_range(c, s, b, &lo, &hi);
-        if (hi > lo && cudaHostUnregister((char *)c->host[b] + lo) != cudaSuccess) cudaGetLastError();
-    }
-    s.host_pinned = false;
+    const int G = (int)c->shards.size();
+    for (int b = s.index; b < BS_BUF_COUNT; b += G)
+        if (c->host[b] && c->host_registered[b]) {
+            if (cudaHostUnregister(c->host[b]) != cudaSuccess) cudaGetLastError();
+            c->host_registered[b] = false;
+        }
 }
 
 // ---- per-device commands (run on the device's own thread) ------------------------------------------
@@ -377,7 +368,6 @@ enum { UP_INPUTS = 1, UP_REFVAL = 2 };
 
 void do_upload(bs_gpu_ctx *c, Shard &s, int what)
 {
-    ensure_pinned(c, s);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     if (what & UP_INPUTS)
         for (int b = BS_BUF_SPTPRICE; b <= BS_BUF_OTYPE; b++) {
@@ -569,7 +559,6 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     const bool chk = c->arg_err_chk != 0;
     const int what = c->arg_upload_what;
     s.h2d_ms = s.roi_ms = s.d2h_ms = s.pipeline_ms = 0;
-    ensure_pinned(c, s);
     if (s.count == 0) { s.err_total = 0; s.list_n = 0; s.list.clear(); return; }
     {
         const int S = price_subshards(c, s);
@@ -666,7 +655,6 @@ void do_price(bs_gpu_ctx *c, Shard &s)
 void do_download(bs_gpu_ctx *c, Shard &s)
 {
     const size_t eb = elem_bytes(c, BS_BUF_PRICES);
-    ensure_pinned(c, s);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     SH_CUDA(cudaMemcpyAsync((char *)c->host[BS_BUF_PRICES] + s.first * eb, s.d[BS_BUF_PRICES], s.count * eb, cudaMemcpyDeviceToHost, s.stream));
     SH_CUDA(cudaEventRecord(s.ev1, s.stream));
@@ -735,7 +723,7 @@ void do_teardown(bs_gpu_ctx *c, Shard &s)
     if (s.stream) cudaStreamSynchronize(s.stream);
     if (s.copy_stream) cudaStreamSynchronize(s.copy_stream);
     if (s.d2h_stream) cudaStreamSynchronize(s.d2h_stream);
-    unpin(c, s);
+    do_unpin(c, s);
     for (auto &kv : s.graphs) cudaGraphExecDestroy(kv.second);
     s.graphs.clear();
     if (s.d_table) cudaFree(s.d_table);
@@ -773,6 +761,7 @@ void device_thread(bs_gpu_ctx *c, int g)
         s.err.clear();
         switch (cmd) {
         case CMD_SETUP: do_setup(c, s); break;
+        case CMD_PIN: do_pin(c, s); break;
         case CMD_UPLOAD: do_upload(c, s, c->arg_upload_what); break;
         case CMD_RUN: do_run(c, s); break;
         case CMD_DOWNLOAD: do_download(c, s); break;
@@ -898,6 +887,15 @@ int broadcast(bs_gpu_ctx *c, int cmd)
     return wait_all(c);
 }
 
+// Pin the staging buffers once, right before the first command that copies from / to them.
+int pin_staging(bs_gpu_ctx *c)
+{
+    if (c->host_pinned || (c->flags & BS_GPU_FLAG_NO_HOST_STAGING)) return BS_GPU_OK;
+    const int st = broadcast(c, CMD_PIN);
+    if (st == BS_GPU_OK) c->host_pinned = true;
+    return st;
+}
+
 double now_ms()
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -988,9 +986,9 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (cfg->devices) c->want_devices.assign(cfg->devices, cfg->devices + cfg->num_gpus);
 
     // Host staging (north_star item 1): page-aligned anonymous memory the loader writes SoA straight into.  It is
-    // available immediately -- no CUDA context is needed to allocate it -- and every device thread pins
-    // (cudaHostRegister, portable) its own page range of every stream right before its first copy, so the
-    // pinning cost is spread over the device threads and the context creation overlaps the file parse.
+    // available immediately -- no CUDA context is needed to allocate it -- and the device threads pin it
+    // (cudaHostRegister, portable; see do_pin) right before the first copy, so the context creation overlaps the
+    // file parse.
     if (!(c->flags & BS_GPU_FLAG_NO_HOST_STAGING)) {
         const size_t page = (size_t)sysconf(_SC_PAGESIZE);
         for (int b = 0; b < BS_BUF_COUNT; b++) {
@@ -1049,6 +1047,10 @@ static int upload_impl(bs_gpu_ctx *c, int what)
     if ((what & UP_REFVAL) && !(c->flags & BS_GPU_FLAG_WITH_DGREFVAL))
         return fail(c, BS_GPU_ERR_STATE, "context was created without the DGREFVAL stream");
     c->arg_upload_what = what;
+    {
+        const int pinned = pin_staging(c);
+        if (pinned != BS_GPU_OK) return pinned;
+    }
     const double t0 = now_ms();
     const int st = broadcast(c, CMD_UPLOAD);
     c->timing.wall_ms = now_ms() - t0;
@@ -1119,6 +1121,10 @@ int bs_gpu_download(bs_gpu_ctx *c)
 {
     if (!c) return BS_GPU_ERR_INVALID;
     if (c->flags & BS_GPU_FLAG_NO_HOST_STAGING) return fail(c, BS_GPU_ERR_STATE, "context has no host staging buffers");
+    {
+        const int pinned = pin_staging(c);
+        if (pinned != BS_GPU_OK) return pinned;
+    }
     const double t0 = now_ms();
     const int st = broadcast(c, CMD_DOWNLOAD);
     c->timing.wall_ms = now_ms() - t0;
@@ -1145,7 +1151,11 @@ int bs_gpu_price(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *n
     c->arg_num_runs = num_runs;
     c->arg_err_chk = err_chk;
     c->arg_upload_what = what;
-    const double t0 = now_ms();
+    const double t0 = now_ms();  // the one-time pinning of the staging buffers is part of the first call's wall time
+    {
+        const int pinned = pin_staging(c);
+        if (pinned != BS_GPU_OK) return pinned;
+    }
     const int st = broadcast(c, CMD_PRICE);
     c->timing.wall_ms = now_ms() - t0;
     if (st != BS_GPU_OK) return st;
