@@ -129,8 +129,9 @@ int main(int argc, char **argv)
     // context creation and arena allocation then run in the background while the rows are parsed.
     // (BS_GPU_FLAG_ASYNC_DISCOVERY would push discovery into the background too, but cuInit's mmap traffic contends
     // with the parser threads' page faults: measured 1.26 s instead of 0.81 s for the 10M-row native file.)
-    // cuInit brings up EVERY visible device (about 0.6 s each on an 8-GPU B200 box): when fewer GPUs are asked for
-    // than the box has, hide the others first -- unless the user set CUDA_VISIBLE_DEVICES, which is left alone.
+    // When fewer GPUs are asked for than the box has, hide the others before CUDA starts -- unless the user set
+    // CUDA_VISIBLE_DEVICES, which is left alone.
+    const double t_cuinit0 = now_s();
     if (!getenv("CUDA_VISIBLE_DEVICES")) {
         const int want = nThreads < 1 ? 1 : nThreads;
         if (count_gpu_device_nodes() > want) {
@@ -273,8 +274,8 @@ int main(int argc, char **argv)
     printf("[BS_GPU] input: %s\n", from_soa ? (openPath == inputFile ? "binary SoA file" : "binary SoA side-car (cache hit)")
                                             : (use_cache ? "text (side-car written)" : "text"));
     bs_gpu_fini(ctx);
-    printf("[BS_GPU] load_s=%.3f (open_s=%.3f init_s=%.3f parse_s=%.3f) write_s=%.3f total_s=%.3f\n", t_loaded - t_begin,
-           t_init0 - t_begin, t_init1 - t_init0, t_loaded - t_init1, t_w1 - t_w0, now_s() - t_begin);
+    printf("[BS_GPU] load_s=%.3f (open_s=%.3f cuinit_s=%.3f init_s=%.3f parse_s=%.3f) write_s=%.3f total_s=%.3f\n", t_loaded - t_begin,
+           t_cuinit0 - t_begin, t_init0 - t_cuinit0, t_init1 - t_init0, t_loaded - t_init1, t_w1 - t_w0, now_s() - t_begin);
 #ifdef ENABLE_PARSEC_HOOKS
     (void)t_roi0;
     (void)t_roi1;
