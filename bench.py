@@ -220,6 +220,10 @@ def ours(args):
     in_process_gpus = 1
     if world == 1 and args.gpus > 1:
         in_process_gpus = args.gpus  # launched without torchrun: one context drives all GPUs (one host thread each)
+    numa_cpus = None
+    if world > 1 and not args.no_numa_bind:
+        from p3arsec_b200.dist import bind_to_gpu_locality
+        numa_cpus = bind_to_gpu_locality(local_rank)  # before any staging memory is touched
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ranks = Ranks(backend="nccl", device=dev)
@@ -346,6 +350,7 @@ def ours(args):
         "config": {"workload": desc, "options_total": int(n_total), "num_runs": NUM_RUNS, "math": launch["math"],
                    "threads_per_block": launch["threads_per_block"], "blocks": launch["blocks"],
                    "parallelism": "%d independent contiguous shards, no collective" % n_gpus,
+                   "numa": ("rank 0 bound to %d GPU-local CPUs" % len(numa_cpus)) if numa_cpus else "no binding",
                    "l2": "inputs+outputs per GPU = %.0f MB vs 126 MB L2 (inputs larger than L2; no flush needed)" % (bpo * n_per_launch / 1e6)
                          if bpo * n_per_launch > 126e6 else "working set fits L2: runs after the first are L2-resident",
                    "step": "one ROI = NUM_RUNS launches over the whole set (blackscholes.c:318)"},
@@ -385,6 +390,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin each rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -21,6 +21,29 @@ def shard_range(n, world, rank):
     return first, q + (1 if rank < r else 0)
 
 
+def bind_to_gpu_locality(gpu_index):
+    """Pin this process to the CPUs that share a NUMA node with GPU `gpu_index` (NVML's ideal CPU affinity), so that the
+    staging buffers it first-touches -- and pins -- live in the memory closest to that GPU's PCIe root.  With eight
+    ranks each copying 280 MB per step, remote-node staging memory is what limits the end-to-end rate.  Returns the
+    CPU list, or None when NVML or the topology is unavailable (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        pynvml.nvmlShutdown()
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 class Ranks:
     """Barrier + reductions over the launched ranks (a no-op group when world_size == 1)."""
 
