@@ -23,7 +23,8 @@
  *                 fp32, the reference's double-literal promotions are not imitated; fp64: explicitly rounded, never
  *                 contracted operations, so only the last ulp of exp()/log() can differ from the fp64 CPU build).
  *   BS_MATH_FAST  fp32: 9 MUFU ops per option (sqrt, rcp x3, lg2 x2, ex2 x3) with log2(e)/ln(2) and 1/sqrt(2 pi)
- *                 folded into constants, Horner form of the degree-5 polynomial.  fp64: bs_math_f64.h.
+ *                 folded into constants, Horner form of the degree-5 polynomial, one Newton step on each
+ *                 reciprocal.  fp64: bs_math_f64.h.
  *   MATH_PROBE    diagnostic only: no pricing, same streams (the bandwidth ceiling of the traffic pattern).
  */
 #pragma once
@@ -84,6 +85,18 @@ __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ft
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// 1/x to <= 1 ulp: MUFU.RCP plus one Newton step.  The raw approximation's last-bit errors are amplified by the
+// degree-5 CNDF polynomial and by d1 = num / den: over 20M random options the step brings the largest distance to the
+// reference output from 8.3e-5 to 7.3e-5 for 0.3 us per 10M-option pass (profiles/r01_fp32_accuracy_knobs.txt).
+// For x = 0 or inf the correction term is NaN (0 * inf) and the raw result (inf or 0) is kept, so the degenerate
+// inputs (t = 0, v = 0) still follow the reference's inf arithmetic.
+__device__ __forceinline__ float rcp_refined(float x)
+{
+    const float r = mufu_rcp(x);
+    const float c = fmaf(r, fmaf(-x, r, 1.0f), r);
+    return (c == c) ? c : r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32, BS_MATH_FAST
 // ---------------------------------------------------------------------------------------------
@@ -98,7 +111,7 @@ __device__ __forceinline__ float cndf_tail_fast(float d)
     const float A5 = 1.330274429f * 0.39894228040143270286f;
     const float NEG_HALF_LOG2E = -0.72134752044448170368f;
 
-    float k = mufu_rcp(fmaf(fabsf(d), 0.2316419f, 1.0f));
+    float k = rcp_refined(fmaf(fabsf(d), 0.2316419f, 1.0f));
     float e = mufu_ex2((d * NEG_HALF_LOG2E) * d);
     float p = fmaf(k, A5, A4);
     p = fmaf(k, p, A3);
@@ -114,7 +127,7 @@ __device__ __forceinline__ float price_fast(float s, float k, float r, float v, 
 
     float sq = mufu_sqrt(t);                         // xSqrtTime            :224
     float den = v * sq;                              // xDen                 :238
-    float rden = mufu_rcp(den);
+    float rden = rcp_refined(den);
     float lg = mufu_lg2(s) - mufu_lg2(k);            // log2(s/k)            :226
     float drift = fmaf(0.5f * v, v, r);              // r + v*v/2            :231-234
     float num = fmaf(lg, LN2, drift * t);            // (..)*t + ln(s/k)     :235-236
