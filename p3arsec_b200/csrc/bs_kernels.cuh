@@ -413,18 +413,22 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
     } else if (g >= groups) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
     } else {
-        Group<FP> cur[UNROLL], nxt[UNROLL];
-        load_trip(cur, g);
+        // two register sets used in turn (ping-pong), so no trip is ever copied from "next" to "current"
+        Group<FP> bufA[UNROLL], bufB[UNROLL];
+        const size_t step = (size_t)UNROLL * stride;
+        load_trip(bufA, g);
         asm volatile("griddepcontrol.wait;" ::: "memory");
         for (;;) {
-            const size_t g_next = g + (size_t)UNROLL * stride;
-            const bool more = g_next < groups;
-            if (more) load_trip(nxt, g_next);  // in flight while this trip is priced
-            price_trip(cur, g);
+            bool more = g + step < groups;
+            if (more) load_trip(bufB, g + step);  // in flight while trip A is priced
+            price_trip(bufA, g);
             if (!more) break;
-#pragma unroll
-            for (int u = 0; u < UNROLL; u++) cur[u] = nxt[u];
-            g = g_next;
+            g += step;
+            more = g + step < groups;
+            if (more) load_trip(bufA, g + step);  // in flight while trip B is priced
+            price_trip(bufB, g);
+            if (!more) break;
+            g += step;
         }
     }
     // ragged tail: the last n % LANES options, one scalar option per thread of block 0
