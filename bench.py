@@ -43,6 +43,8 @@ WORKLOADS = {
     "native_fp64": (10_000_000, 8, "weak", "blackscholes native 10M options, fptype=double, NUM_RUNS=100 per GPU"),
     "synth1b": (1_000_000_000, 4, "strong", "synthetic 1B-option fp32 set (inputgen distribution) sharded over the GPUs, NUM_RUNS=100"),
 }
+# the sibling Map has its own tool with the same JSON contract: `--workload swaptions_<set>` forwards to it
+SW_WORKLOADS = ("native", "simlarge", "simmedium", "simsmall")
 CPU_SAMPLE_OPTIONS = 2_000_000  # bounded sample for the CPU reference: 2M options x 100 runs
 
 
@@ -365,7 +367,7 @@ def ensure_built():
     """Built artefacts are git-ignored; if this checkout has none yet, build them once (nvcc is part of the image)."""
     lib = os.path.join(ROOT, "p3arsec_b200", "lib", "libbs_gpu.so")
     gen = os.path.join(ROOT, "p3arsec_b200", "bin", "bs_inputgen")
-    if os.path.exists(lib) and os.path.exists(gen):
+    if os.path.exists(lib) and os.path.exists(gen) and os.path.exists(os.path.join(ROOT, "p3arsec_b200", "lib", "libsw_gpu.so")):
         return
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         import __graft_entry__
@@ -384,7 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="native")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["swaptions_" + w for w in SW_WORKLOADS], default="native")
     ap.add_argument("--math", choices=["default", "ieee", "fast"], default="default")
     ap.add_argument("--unroll", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -392,6 +394,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin each rank to its GPU's NUMA node")
     args = ap.parse_args()
+    if args.workload.startswith("swaptions_"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sw_bench
+        return sw_bench.main(["--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl,
+                              "--workload", args.workload[len("swaptions_"):]] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

@@ -15,7 +15,7 @@
 #include <stdio.h>
 #include <time.h>
 
-enum __parsec_benchmark { __parsec_blackscholes = 1 };
+enum __parsec_benchmark { __parsec_blackscholes = 1, __parsec_swaptions = 10 };
 
 static double bs_shim_t_begin_;
 static double bs_shim_t_end_;

@@ -1,0 +1,383 @@
+/*
+ * sw_gpu.cu -- implementation of the C ABI in include/sw_gpu.h (libsw_gpu.so): the swaptions Map on B200.
+ *
+ * Reference citations are relative to /root/reference/parsec-ff/pkgs/apps/swaptions/src/ (HSB: =
+ * HJM_Swaption_Blocking.cpp, SEC: = HJM_Securities.cpp).
+ *
+ * Host side of one sw_gpu_price() call:
+ *   1. per swaption, everything HJM_Swaption_Blocking computes before its trial loop (HSB:48-61,116-148: time
+ *      indices, the swap payoff vector, the forward curve and the drifts) is evaluated here with the reference's own
+ *      expressions and packed into one swk::SwParams record (~1.2 KB) in pinned memory;
+ *   2. swaptions are split contiguously over the devices (the static partition of SEC:312 / worker() SEC:100-118);
+ *      each device receives its records (H2D), runs the simulation kernel over (swaption, trial-chunk) work items
+ *      and the per-swaption finalize kernel, and returns mean / standard error (D2H) -- all asynchronous on the
+ *      device's own stream, so the devices work at the same time under one caller thread;
+ *   3. the call returns when every device has finished.  Device time is taken with CUDA events on those streams.
+ * No inter-device traffic, no collective, no CPU fallback.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sw_gpu.h"
+#include "sw_kernels.cuh"
+
+namespace {
+
+struct Dev {
+    int device = 0;
+    int sm_count = 0;
+    int first = 0, count = 0;  // shard of the last call
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    swk::SwParams *d_params = nullptr;
+    double2 *d_partials = nullptr;
+    size_t partial_cap = 0;
+    double *d_out = nullptr;  // [mean(max) | err(max)]
+    int occ_fast = 0, occ_lean = 0, occ_generic = 0;
+    float roi_ms = 0;
+};
+
+}  // namespace
+
+struct sw_gpu_ctx {
+    int max_swaptions = 0, iN = 0, iFactors = 0;
+    std::vector<Dev> devs;
+    swk::SwParams *h_params = nullptr;  // pinned, max_swaptions records
+    double *h_out = nullptr;            // pinned, 2 x max_swaptions
+    int cfg_ctas_per_sm = 0, cfg_tpt = 0;
+    int shards_used = 0;
+    sw_gpu_timing timing;
+    std::string err;
+    sw_gpu_ctx() { memset(&timing, 0, sizeof(timing)); }
+};
+
+namespace {
+
+int fail(sw_gpu_ctx *c, int status, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return status;
+}
+
+#define SW_CUDA(c, call)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail((c), e_ == cudaErrorMemoryAllocation ? SW_GPU_ERR_NOMEM : SW_GPU_ERR_CUDA, "%s: %s", \
+                        #call, cudaGetErrorString(e_));                                                       \
+    } while (0)
+
+// Everything HJM_Swaption_Blocking derives before the trial loop.  Returns false where the reference would index
+// outside its vectors (it has no checks of its own).
+bool prepare(swk::SwParams &P, const sw_gpu_swaption &s, int iN, int iFactors, const double *pdYield,
+             const double *ppdFactors, long seed, long lTrials, int BLOCKSIZE)
+{
+    memset(&P, 0, sizeof(P));
+    const double ddelt = (double)(s.dYears / iN);                                  // HSB:48
+    if (!(ddelt > 0.0) || !std::isfinite(ddelt)) return false;
+    const double fr = s.dPaymentInterval / ddelt + 0.5, st = s.dMaturity / ddelt + 0.5, tp = s.dTenor / ddelt + 0.5;
+    const double vl = iN - s.dMaturity / ddelt + 0.5;
+    if (!(fabs(fr) < 1e6 && fabs(st) < 1e6 && fabs(tp) < 1e6 && fabs(vl) < 1e6)) return false;
+    const int iFreqRatio = (int)fr;                                                // HSB:50
+    double dStrikeCont;
+    if (s.dCompounding == 0) dStrikeCont = s.dStrike;                              // HSB:56-57
+    else dStrikeCont = (1 / s.dCompounding) * log(1 + s.dStrike * s.dCompounding);  // HSB:61
+    const int iSwapVectorLength = (int)vl;                                         // HSB:116
+    const int iSwapStartTimeIndex = (int)st;                                       // HSB:125
+    const int iSwapTimePoints = (int)tp;                                           // HSB:126
+    const double dSwapVectorYears = (double)(iSwapVectorLength * ddelt);           // HSB:127
+    if (iSwapVectorLength < 1 || iSwapVectorLength > iN || iSwapStartTimeIndex < 0 || iSwapStartTimeIndex > iN - 1 ||
+        iFreqRatio < 1 || iSwapTimePoints > iSwapVectorLength - 1)
+        return false;
+
+    for (int i = iFreqRatio; i <= iSwapTimePoints; i += iFreqRatio) {              // HSB:134-140
+        if (i != iSwapTimePoints) P.pay[i] = exp(dStrikeCont * s.dPaymentInterval) - 1;
+        if (i == iSwapTimePoints) P.pay[i] = exp(dStrikeCont * s.dPaymentInterval);
+    }
+    // HJM_Yield_to_Forward (HSB:143): f(0) = y(0), f(i) = (i+1) y(i) - i y(i-1)
+    P.fwd[0] = pdYield[0];
+    for (int i = 1; i <= iN - 1; ++i) P.fwd[i] = (i + 1) * pdYield[i] - i * pdYield[i - 1];
+    // HJM_Drifts (HSB:148): per-factor no-arbitrage drifts, summed over the factors in factor order
+    double drifts[swk::MAXF][swk::MAXN];
+    for (int i = 0; i < iFactors; ++i) {
+        const double *f = ppdFactors + (size_t)i * (iN - 1);
+        drifts[i][0] = 0.5 * ddelt * (f[0]) * (f[0]);
+        for (int j = 1; j <= iN - 2; ++j) {
+            double d = 0;
+            for (int l = 0; l <= j - 1; ++l) d -= drifts[i][l];
+            double dSumVol = 0;
+            for (int l = 0; l <= j; ++l) dSumVol += f[l];
+            d += 0.5 * ddelt * (dSumVol) * (dSumVol);
+            drifts[i][j] = d;
+        }
+        for (int l = 0; l <= iN - 2; ++l) P.fac[i][l] = f[l];
+    }
+    for (int l = 0; l <= iN - 2; ++l) {
+        double tot = 0;
+        for (int i = 0; i < iFactors; ++i) tot += drifts[i][l];
+        P.driftdt[l] = tot * ddelt;  // the product inside HJM_SimPath_Forward_Blocking's path update
+    }
+    P.ddelt = ddelt;
+    P.sqrt_ddelt = sqrt(ddelt);
+    P.swap_ddelt = (double)(dSwapVectorYears / iSwapVectorLength);
+    P.seed = seed;
+    P.trials = lTrials;
+    P.sims = lTrials <= 0 ? 0 : ((lTrials + BLOCKSIZE - 1) / BLOCKSIZE) * (long long)BLOCKSIZE;   // HSB:156
+    P.start = iSwapStartTimeIndex;
+    P.len = iSwapVectorLength;
+    P.last_pay = iSwapTimePoints;
+    return true;
+}
+
+enum Kind { K_FAST = 0, K_LEAN = 1, K_GENERIC = 2 };
+
+}  // namespace
+
+extern "C" {
+
+int sw_gpu_abi_version(void) { return SW_GPU_ABI_VERSION; }
+
+const char *sw_gpu_status_string(int status)
+{
+    switch (status) {
+        case SW_GPU_OK: return "ok";
+        case SW_GPU_ERR_INVALID: return "invalid argument";
+        case SW_GPU_ERR_NO_DEVICE: return "no CUDA device";
+        case SW_GPU_ERR_CUDA: return "CUDA error";
+        case SW_GPU_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+int sw_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *sw_gpu_last_error(sw_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void sw_gpu_fini(sw_gpu_ctx *ctx)
+{
+    if (!ctx) return;
+    for (Dev &d : ctx->devs) {
+        if (cudaSetDevice(d.device) != cudaSuccess) continue;
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.d_params) cudaFree(d.d_params);
+        if (d.d_partials) cudaFree(d.d_partials);
+        if (d.d_out) cudaFree(d.d_out);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    delete ctx;
+}
+
+static int init_impl(sw_gpu_ctx *c, const int *devices, int num_gpus)
+{
+    int visible = sw_gpu_device_count();
+    if (visible <= 0) return fail(c, SW_GPU_ERR_NO_DEVICE, "no CUDA device visible (libsw_gpu has no CPU fallback)");
+    if (!devices && num_gpus > visible) num_gpus = visible;  // like the blackscholes driver: clamp to what the box has
+    c->devs.resize(num_gpus);
+    const size_t n = (size_t)c->max_swaptions;
+    for (int g = 0; g < num_gpus; ++g) {
+        Dev &d = c->devs[g];
+        d.device = devices ? devices[g] : g;
+        if (d.device < 0 || d.device >= visible) return fail(c, SW_GPU_ERR_NO_DEVICE, "device ordinal %d not present (%d visible)", d.device, visible);
+        SW_CUDA(c, cudaSetDevice(d.device));
+        cudaDeviceProp prop;
+        SW_CUDA(c, cudaGetDeviceProperties(&prop, d.device));
+        if (prop.major < 10) return fail(c, SW_GPU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", d.device, prop.major, prop.minor);
+        d.sm_count = prop.multiProcessorCount;
+        SW_CUDA(c, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        SW_CUDA(c, cudaEventCreate(&d.ev0));
+        SW_CUDA(c, cudaEventCreate(&d.ev1));
+        SW_CUDA(c, cudaMalloc(&d.d_params, n * sizeof(swk::SwParams)));
+        SW_CUDA(c, cudaMalloc(&d.d_out, 2 * n * sizeof(double)));
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fast, swk::sw_sim_fast<false>, swk::THREADS, sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean, swk::sw_sim_fast<true>, swk::THREADS, sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_generic, swk::sw_sim_generic, swk::THREADS, 0));
+        if (d.occ_fast < 1 || d.occ_lean < 1 || d.occ_generic < 1) return fail(c, SW_GPU_ERR_CUDA, "a kernel does not fit on device %d", d.device);
+    }
+    SW_CUDA(c, cudaHostAlloc(&c->h_params, n * sizeof(swk::SwParams), cudaHostAllocPortable));
+    SW_CUDA(c, cudaHostAlloc(&c->h_out, 2 * n * sizeof(double), cudaHostAllocPortable));
+    return SW_GPU_OK;
+}
+
+int sw_gpu_init(sw_gpu_ctx **out, int num_gpus, int max_swaptions, int iN, int iFactors)
+{
+    return sw_gpu_init_devices(out, nullptr, num_gpus, max_swaptions, iN, iFactors);
+}
+
+int sw_gpu_init_devices(sw_gpu_ctx **out, const int *devices, int num_gpus, int max_swaptions, int iN, int iFactors)
+{
+    if (!out) return SW_GPU_ERR_INVALID;
+    *out = nullptr;
+    if (num_gpus < 1 || max_swaptions < 1 || iN < 2 || iN > SW_GPU_MAX_N || iFactors < 1 || iFactors > SW_GPU_MAX_FACTORS)
+        return SW_GPU_ERR_INVALID;
+    sw_gpu_ctx *c = new (std::nothrow) sw_gpu_ctx();
+    if (!c) return SW_GPU_ERR_NOMEM;
+    c->max_swaptions = max_swaptions;
+    c->iN = iN;
+    c->iFactors = iFactors;
+    int st = init_impl(c, devices, num_gpus);
+    if (st != SW_GPU_OK) {
+        fprintf(stderr, "sw_gpu_init: %s\n", c->err.c_str());
+        sw_gpu_fini(c);
+        return st;
+    }
+    *out = c;
+    return SW_GPU_OK;
+}
+
+int sw_gpu_set_geometry(sw_gpu_ctx *c, int ctas_per_sm, int trials_per_thread)
+{
+    if (!c || ctas_per_sm < 0 || trials_per_thread < 0) return SW_GPU_ERR_INVALID;
+    c->cfg_ctas_per_sm = ctas_per_sm;
+    c->cfg_tpt = trials_per_thread;
+    return SW_GPU_OK;
+}
+
+int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions, const double *pdYield,
+                 const double *ppdFactors, long swaption_seed, long lTrials, int BLOCKSIZE, unsigned flags, double *mean,
+                 double *std_error)
+{
+    if (!c) return SW_GPU_ERR_INVALID;
+    if (nSwaptions < 0 || nSwaptions > c->max_swaptions || (nSwaptions > 0 && (!swaptions || !pdYield || !ppdFactors || !mean || !std_error)))
+        return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: bad arguments (nSwaptions = %d, capacity %d)", nSwaptions, c->max_swaptions);
+    if (BLOCKSIZE < 1 || lTrials < 0) return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: BLOCKSIZE %d, lTrials %ld", BLOCKSIZE, lTrials);
+    if (flags & ~(SW_GPU_FLAG_IEEE | SW_GPU_FLAG_LEAN)) return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: unknown flags 0x%x", flags);
+    const auto w0 = std::chrono::steady_clock::now();
+    memset(&c->timing, 0, sizeof(c->timing));
+    c->shards_used = 0;
+    if (nSwaptions == 0) return SW_GPU_OK;
+
+    const int iN = c->iN, nF = c->iFactors;
+    const long long draws = (long long)(iN - 1) * nF;
+    long long sims = 0;
+    for (int i = 0; i < nSwaptions; ++i) {
+        if (!prepare(c->h_params[i], swaptions[i], iN, nF, pdYield + (size_t)i * iN, ppdFactors + (size_t)i * nF * (iN - 1),
+                     swaption_seed + i, lTrials, BLOCKSIZE))
+            return fail(c, SW_GPU_ERR_INVALID, "swaption %d: dYears/dMaturity/dTenor/dPaymentInterval put a time index outside the %d-point HJM path", i, iN);
+        sims = c->h_params[i].sims;
+    }
+    // the fast kernels: the reference drivers' shape, counters inside the range of the 32-bit residue arithmetic
+    Kind kind = K_GENERIC;
+    if (!(flags & SW_GPU_FLAG_IEEE) && iN == swk::FN && nF == swk::FF && swaption_seed >= 0 &&
+        (double)swaption_seed + (double)nSwaptions + (double)sims * (double)draws < 1099511627776.0 /* 2^40 */)
+        kind = (flags & SW_GPU_FLAG_LEAN) ? K_LEAN : K_FAST;
+
+    const int G = std::min<int>((int)c->devs.size(), nSwaptions);
+    const int q = nSwaptions / G, r = nSwaptions % G;
+    int first = 0;
+    for (int g = 0; g < G; ++g) {
+        Dev &d = c->devs[g];
+        d.first = first;
+        d.count = q + (g < r ? 1 : 0);
+        first += d.count;
+
+        const int occ = kind == K_FAST ? d.occ_fast : kind == K_LEAN ? d.occ_lean : d.occ_generic;
+        const int per_sm = c->cfg_ctas_per_sm > 0 ? std::min(c->cfg_ctas_per_sm, occ) : occ;
+        const long long grid_threads = (long long)d.sm_count * per_sm * swk::THREADS;
+        // trials per thread per item: enough items for ~8 per resident CTA (static round-robin balance), capped
+        int tpt = c->cfg_tpt;
+        if (tpt <= 0) {
+            const long long want = (sims * d.count) / (grid_threads * 8);
+            tpt = (int)std::max<long long>(1, std::min<long long>(64, want));
+        }
+        swk::Geom geo;
+        geo.iN = iN;
+        geo.iFactors = nF;
+        geo.tpt = tpt;
+        geo.chunk_trials = (long long)swk::THREADS * tpt;
+        const long long chunks = std::max<long long>(1, (sims + geo.chunk_trials - 1) / geo.chunk_trials);
+        if (chunks * d.count > 0x7fffffffLL) return fail(c, SW_GPU_ERR_INVALID, "too many work items");
+        geo.chunks = (int)chunks;
+        geo.items = (int)(chunks * d.count);
+        const int blocks = (int)std::min<long long>(geo.items, (long long)d.sm_count * per_sm);
+
+        SW_CUDA(c, cudaSetDevice(d.device));
+        if ((size_t)geo.items > d.partial_cap) {
+            if (d.d_partials) SW_CUDA(c, cudaFree(d.d_partials));
+            d.d_partials = nullptr;
+            d.partial_cap = 0;
+            SW_CUDA(c, cudaMalloc(&d.d_partials, (size_t)geo.items * sizeof(double2)));
+            d.partial_cap = (size_t)geo.items;
+        }
+        SW_CUDA(c, cudaMemcpyAsync(d.d_params, c->h_params + d.first, (size_t)d.count * sizeof(swk::SwParams), cudaMemcpyHostToDevice, d.stream));
+        SW_CUDA(c, cudaEventRecord(d.ev0, d.stream));
+        if (kind == K_FAST)
+            swk::sw_sim_fast<false><<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
+        else if (kind == K_LEAN)
+            swk::sw_sim_fast<true><<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
+        else
+            swk::sw_sim_generic<<<blocks, swk::THREADS, 0, d.stream>>>(d.d_params, geo, d.d_partials);
+        SW_CUDA(c, cudaGetLastError());
+        swk::sw_finalize<<<d.count, swk::THREADS, 0, d.stream>>>(d.d_params, geo, d.d_partials, d.d_out, d.d_out + c->max_swaptions);
+        SW_CUDA(c, cudaGetLastError());
+        SW_CUDA(c, cudaEventRecord(d.ev1, d.stream));
+        SW_CUDA(c, cudaMemcpyAsync(c->h_out + d.first, d.d_out, (size_t)d.count * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        SW_CUDA(c, cudaMemcpyAsync(c->h_out + c->max_swaptions + d.first, d.d_out + c->max_swaptions, (size_t)d.count * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        c->timing.kernel_launches += 2;
+        c->timing.h2d_bytes += (unsigned long long)d.count * sizeof(swk::SwParams);
+        c->timing.d2h_bytes += (unsigned long long)d.count * 2 * sizeof(double);
+    }
+    c->shards_used = G;
+    double roi = 0;
+    for (int g = 0; g < G; ++g) {
+        Dev &d = c->devs[g];
+        SW_CUDA(c, cudaSetDevice(d.device));
+        SW_CUDA(c, cudaStreamSynchronize(d.stream));
+        SW_CUDA(c, cudaEventElapsedTime(&d.roi_ms, d.ev0, d.ev1));
+        roi = std::max(roi, (double)d.roi_ms);
+    }
+    memcpy(mean, c->h_out, (size_t)nSwaptions * sizeof(double));
+    memcpy(std_error, c->h_out + c->max_swaptions, (size_t)nSwaptions * sizeof(double));
+    c->timing.roi_ms = roi;
+    c->timing.trials_simulated = (unsigned long long)sims * (unsigned long long)nSwaptions;
+    c->timing.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return SW_GPU_OK;
+}
+
+int sw_gpu_get_timing(sw_gpu_ctx *c, sw_gpu_timing *out)
+{
+    if (!c || !out) return SW_GPU_ERR_INVALID;
+    *out = c->timing;
+    return SW_GPU_OK;
+}
+
+int sw_gpu_num_shards(sw_gpu_ctx *c) { return c ? c->shards_used : SW_GPU_ERR_INVALID; }
+
+int sw_gpu_shard(sw_gpu_ctx *c, int g, int *device, int *first, int *count)
+{
+    if (!c || g < 0 || g >= c->shards_used) return SW_GPU_ERR_INVALID;
+    if (device) *device = c->devs[g].device;
+    if (first) *first = c->devs[g].first;
+    if (count) *count = c->devs[g].count;
+    return SW_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+/*
+ * sw_kernels.cuh -- sm_100a kernels of the swaptions Map (HJM Monte-Carlo, fp64).
+ *
+ * Reference body: parsec-ff/pkgs/apps/swaptions/src/HJM_Swaption_Blocking.cpp:20-222 (cited as HSB: below) and the
+ * PARSEC-owned leaves it calls (RanUnif, CumNormalInv, HJM_SimPath_Forward_Blocking, Discount_Factors_Blocking;
+ * absent from the overlay, semantics as restated in oracle/sw_absent/).
+ *
+ * Work decomposition.  A trial is independent of every other trial: RanUnif's state is a counter and draw k is a
+ * pure function of (seed + k), so trial t of a swaption reads draws [30 t, 30 t + 30) (iN = 11, iFactors = 3).
+ * A work item = (swaption, chunk of THREADS x trials_per_thread consecutive-strided trials); persistent CTAs take
+ * items round-robin (all items cost the same, so the static schedule is balanced to one item), every thread
+ * simulates its trials one after the other and keeps two fp64 sums; one block reduction per item writes
+ * partial[item] = {sum, sum of squares}; sw_finalize adds the partials of each swaption in a fixed tree and applies
+ * HSB:212-214.  No atomics on the data path: the result is deterministic for a given geometry.
+ *
+ * This is an FP64-pipe-bound kernel (no tensor cores: nothing is a contraction; ~2 KB of parameters per swaption
+ * and 16 bytes of output per item, so HBM is idle).  sw_sim_fast keeps the per-trial state in registers and its
+ * 30 normals in shared memory ([draw][thread], conflict-free); the CumNormalInv tail branch (16 % of the draws,
+ * two logarithms) is deferred and executed only for the draws that need it instead of diverging 30 times.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "bs_math_f64.h"
+
+namespace swk {
+
+constexpr int MAXN = 32;  // SW_GPU_MAX_N
+constexpr int MAXF = 8;   // SW_GPU_MAX_FACTORS
+constexpr int THREADS = 128;
+
+// Everything HJM_Swaption_Blocking derives from its arguments before the trial loop (HSB:48-61,116-148), computed
+// on the host with the reference's own expressions, one record per swaption.
+struct SwParams {
+    double fwd[MAXN];            // HJM_Yield_to_Forward (HSB:143)
+    double driftdt[MAXN];        // pdTotalDrift[l] * ddelt (HSB:148 + the product inside HJM_SimPath_Forward_Blocking)
+    double fac[MAXF][MAXN];      // ppdFactors
+    double pay[MAXN];            // pdSwapPayoffs, zero beyond iSwapVectorLength (HSB:132-140)
+    double ddelt;                // HSB:48
+    double sqrt_ddelt;           // HJM_SimPath_Forward_Blocking
+    double swap_ddelt;           // dSwapVectorYears / iSwapVectorLength (Discount_Factors_Blocking at HSB:184)
+    double inv_trials_unused;
+    long long seed;              // swaption_seed + i (HJM_Securities.cpp:319)
+    long long trials;            // lTrials
+    long long sims;              // ceil(lTrials / BLOCKSIZE) * BLOCKSIZE (HSB:156)
+    int start;                   // iSwapStartTimeIndex (HSB:125)
+    int len;                     // iSwapVectorLength (HSB:116)
+    int last_pay;                // iSwapTimePoints (HSB:126)
+    int pad;
+};
+
+struct Geom {
+    int iN, iFactors;
+    int chunks;            // work items per swaption
+    int items;             // chunks * swaptions on this device
+    int tpt;               // trials per thread per item
+    long long chunk_trials;  // THREADS * tpt
+};
+
+// ---- RanUnif (PARSEC RanUnif.c as restated in oracle/sw_absent/sw_leaves.c), literal 64-bit arithmetic ----------
+__device__ __forceinline__ double ranunif_literal(long long ctr)
+{
+    long long ix = ctr;
+    ix *= 1513517LL;
+    ix %= 2147483647LL;
+    long long k1 = ix / 127773LL;
+    ix = 16807LL * (ix - k1 * 127773LL) - k1 * 2836LL;
+    if (ix < 0) ix = ix + 2147483647LL;
+    return (double)ix * 4.656612875e-10;
+}
+
+// Same draw for counters in [0, 2^40): x = ctr * 1513517 mod (2^31 - 1) kept as a 32-bit residue that advances by
+// +1513517 per draw, and Schrage's step 16807 x mod (2^31 - 1) (exactly what the k1/127773/2836 dance computes
+// for x in [0, 2^31 - 1)) done with one 64-bit product and a Mersenne fold.
+constexpr uint32_t RU_M = 2147483647u;
+__device__ __forceinline__ uint32_t mersenne31(uint64_t p)  // p < 2^62
+{
+    uint64_t s = (p & RU_M) + (p >> 31);
+    s = (s & RU_M) + (s >> 31);
+    uint32_t r = (uint32_t)s;
+    return r >= RU_M ? r - RU_M : r;
+}
+__device__ __forceinline__ uint32_t ru_residue(long long ctr) { return mersenne31((uint64_t)ctr * 1513517ull); }
+__device__ __forceinline__ uint32_t ru_next(uint32_t x)
+{
+    x += 1513517u;
+    return x >= RU_M ? x - RU_M : x;
+}
+__device__ __forceinline__ double ru_draw(uint32_t x)
+{
+    uint64_t p = (uint64_t)x * 16807ull;  // < 2^46
+    uint32_t s = (uint32_t)(p & RU_M) + (uint32_t)(p >> 31);
+    s = s >= RU_M ? s - RU_M : s;
+    return (double)(int)s * 4.656612875e-10;
+}
+
+// Moro's coefficients; deliberately not const (see bs_tables_f64.h: const __constant__ doubles come back as
+// 64-bit immediates that cost two UMOVs per use).
+static __device__ __constant__ double MORO_A[4] = {2.50662823884, -18.61500062529, 41.39119773534, -25.44106049637};
+static __device__ __constant__ double MORO_B[4] = {-8.47351093090, 23.08336743743, -21.06224101826, 3.13082909833};
+static __device__ __constant__ double MORO_C[9] = {0.3374754822726147, 0.9761690190917186, 0.1607979714918209,
+                                                   0.0276438810333863, 0.0038405729373609, 0.0003951896511919,
+                                                   0.0000321767881768, 0.0000002888167364, 0.0000003960315187};
+
+// ---- CumNormalInv in the reference's operation order, every operation rounded on its own --------------------------
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+__device__ __noinline__ double cumnormalinv_ieee(double u)
+{
+    double x = add_rn(u, -0.5);
+    if (fabs(x) < 0.42) {
+        double r = mul_rn(x, x);
+        double num = add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(MORO_A[3], r), MORO_A[2]), r), MORO_A[1]), r), MORO_A[0]);
+        double den = add_rn(
+            mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(MORO_B[3], r), MORO_B[2]), r), MORO_B[1]), r), MORO_B[0]), r),
+            1.0);
+        return __ddiv_rn(mul_rn(x, num), den);
+    }
+    double r = u;
+    if (x > 0.0) r = add_rn(1.0, -u);
+    r = log(-log(r));
+    double p = MORO_C[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) p = add_rn(MORO_C[i], mul_rn(r, p));
+    return x < 0.0 ? -p : p;
+}
+
+// exp for the fast kernel: the table-driven block for every argument the simulation can produce, libdevice for the
+// rest (|x| >= 700, inf, NaN -- reached only after a draw of exactly 0, see the tail below).
+__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+__device__ __forceinline__ double exp_guarded(double x, const double *tab)
+{
+    if (!(fabs(x) < 700.0)) return exp_slow(x);
+    return bsm::exp_f64(x, tab);
+}
+
+// Block-wide sum of two doubles; result valid in thread 0.
+__device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[THREADS / 32])
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[0][w] = a;
+        red[1][w] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = red[0][0];
+        b = red[1][0];
+#pragma unroll
+        for (int i = 1; i < THREADS / 32; ++i) {
+            a += red[0][i];
+            b += red[1][i];
+        }
+    }
+}
+
+// =====================================================================================================================
+// sw_sim_fast: iN = 11, iFactors = 3 (the only shape the reference drivers create: HJM_Securities.cpp:56,58).
+// =====================================================================================================================
+constexpr int FN = 11, FF = 3, FD = (FN - 1) * FF;
+
+struct FastShared {
+    double tab[bsm::TAB_DOUBLES];
+    double z[FD][THREADS];
+    double fwd[FN];
+    double driftdt[FN - 1];
+    double fac[FF][FN - 1];  // pre-multiplied by sqrt_ddelt
+    double pay[FN];
+    double red[2][THREADS / 32];
+};
+
+template <bool LEAN>
+__global__ void __launch_bounds__(THREADS, 4)
+sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
+    const int tid = threadIdx.x;
+    bsm::fill_tables(sh.tab, tid, THREADS);
+
+    int cur = -1;
+    double ddelt = 0, swap_ddelt = 0;
+    long long seed = 0, sims = 0;
+    int start = 0, len = 0, last_pay = 0;
+
+    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const int sw = item / g.chunks, chunk = item - sw * g.chunks;
+        __syncthreads();  // previous item's reduction and parameter reads are done
+        if (sw != cur) {
+            const SwParams &P = params[sw];
+            if (tid < FN) {
+                sh.fwd[tid] = P.fwd[tid];
+                sh.pay[tid] = P.pay[tid];
+            }
+            if (tid < FN - 1) sh.driftdt[tid] = P.driftdt[tid];
+            if (tid >= 32 && tid < 32 + FF * (FN - 1)) {
+                const int k = tid - 32, i = k / (FN - 1), l = k - i * (FN - 1);
+                sh.fac[i][l] = P.fac[i][l] * P.sqrt_ddelt;
+            }
+            ddelt = P.ddelt;
+            swap_ddelt = P.swap_ddelt;
+            seed = P.seed;
+            sims = P.sims;
+            start = P.start;
+            len = P.len;
+            last_pay = P.last_pay;
+            cur = sw;
+        }
+        __syncthreads();
+
+        const int steps = LEAN ? start : FN - 1;             // time steps whose shocks are needed
+        const int swap_end = LEAN ? last_pay : len - 1;      // last swap discount factor needed
+        double sum = 0.0, sumsq = 0.0;
+
+        for (int m = 0; m < g.tpt; ++m) {
+            const long long t = (long long)chunk * g.chunk_trials + (long long)m * THREADS + tid;
+            if (t >= sims) break;
+
+            // ---- phase A: the trial's normals.  Central branch for every draw; tail draws are noted in a mask and
+            // redone afterwards, so a warp pays for max-over-lanes(#tail draws) tail evaluations, not for 30.
+            uint32_t x = ru_residue(seed + t * FD);
+            uint32_t tail = 0;
+            const int ndraw = steps * FF;
+            for (int k = 0; k < ndraw; ++k) {
+                const double u = ru_draw(x);
+                x = ru_next(x);
+                const double xc = u - 0.5;
+                const double r = xc * xc;
+                double num = fma(MORO_A[3], r, MORO_A[2]);
+                num = fma(num, r, MORO_A[1]);
+                num = fma(num, r, MORO_A[0]);
+                double den = fma(MORO_B[3], r, MORO_B[2]);
+                den = fma(den, r, MORO_B[1]);
+                den = fma(den, r, MORO_B[0]);
+                den = fma(den, r, 1.0);
+                // tail draws (|xc| >= 0.42): keep u itself in the slot (the value the tail pass needs) and note the slot
+                const bool is_tail = !(fabs(xc) < 0.42);
+                const double zc = (xc * num) * bsm::rcp_f64(is_tail ? 1.0 : den);
+                sh.z[k][tid] = is_tail ? u : zc;
+                tail |= (is_tail ? 1u : 0u) << k;
+            }
+            while (tail) {
+                const int k = __ffs(tail) - 1;
+                tail &= tail - 1;
+                const double u = sh.z[k][tid];
+                const bool upper = u > 0.5;
+                double r = upper ? 1.0 - u : u;
+                double zt;
+                if (r > 0.0) {
+                    r = bsm::log_f64(-bsm::log_f64(r, sh.tab), sh.tab);
+                    double p = fma(r, MORO_C[8], MORO_C[7]);
+                    p = fma(r, p, MORO_C[6]);
+                    p = fma(r, p, MORO_C[5]);
+                    p = fma(r, p, MORO_C[4]);
+                    p = fma(r, p, MORO_C[3]);
+                    p = fma(r, p, MORO_C[2]);
+                    p = fma(r, p, MORO_C[1]);
+                    zt = fma(r, p, MORO_C[0]);
+                } else {
+                    zt = INFINITY;  // u == 0 (counter a multiple of 2^31 - 1): log(-log(0)) = +inf in the reference
+                }
+                sh.z[k][tid] = upper ? zt : -zt;
+            }
+
+            // ---- phase B: the forward-rate path, row by row (HJM_SimPath_Forward_Blocking), with column 0 feeding the
+            // payoff discount factor (HSB:167-172) and row `start` kept for the swap leg (HSB:179-183)
+            double row[FN], srow[FN];
+#pragma unroll
+            for (int l = 0; l < FN; ++l) {
+                row[l] = sh.fwd[l];
+                srow[l] = row[l];  // start == 0
+            }
+            double run = 1.0, pay_df = 1.0;
+#pragma unroll
+            for (int j = 1; j <= FN - 1; ++j) {
+                if (j <= steps || !LEAN) {
+                    if (!LEAN || j <= start) {
+                        run *= exp_guarded(-row[0] * ddelt, sh.tab);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
+                        if (j == start) pay_df = run;
+                    }
+                    const double z0 = sh.z[FF * (j - 1) + 0][tid];
+                    const double z1 = sh.z[FF * (j - 1) + 1][tid];
+                    const double z2 = sh.z[FF * (j - 1) + 2][tid];
+#pragma unroll
+                    for (int l = 0; l <= FN - 1 - j; ++l) {
+                        double shock = sh.fac[0][l] * z0;
+                        shock = fma(sh.fac[1][l], z1, shock);
+                        shock = fma(sh.fac[2][l], z2, shock);
+                        row[l] = (row[l + 1] + sh.driftdt[l]) + shock;
+                    }
+                    row[FN - j] = 0.0;  // the reference's path matrix is zero beyond the triangle
+                    if (j == start) {
+#pragma unroll
+                        for (int l = 0; l < FN; ++l) srow[l] = row[l];
+                    }
+                }
+            }
+
+            // ---- swap leg: DF[i] = prod_{k<i} exp(-srow[k] swap_ddelt); fixed leg = sum pay[i] DF[i] (HSB:184-195)
+            double df = 1.0, fixed = 0.0;
+#pragma unroll
+            for (int i = 1; i <= FN - 1; ++i) {
+                if (i <= swap_end) {
+                    df *= exp_guarded(-srow[i - 1] * swap_ddelt, sh.tab);
+                    fixed = fma(sh.pay[i], df, fixed);
+                }
+            }
+            const double payoff = fixed - 1.0 > 0.0 ? fixed - 1.0 : 0.0;  // dMax (HSB:196)
+            const double disc = payoff * pay_df;                          // HSB:198
+            sum += disc;                                                  // HSB:203
+            sumsq = fma(disc, disc, sumsq);                               // HSB:204
+        }
+
+        block_sum2(sum, sumsq, sh.red);
+        if (tid == 0) partials[item] = make_double2(sum, sumsq);
+    }
+}
+
+// =====================================================================================================================
+// sw_sim_generic: any iN <= 32, iFactors <= 8; libdevice exp/log, IEEE divide, every operation rounded on its own in
+// the reference's order.  One trial per thread at a time, path rows in local memory.
+// =====================================================================================================================
+__global__ void __launch_bounds__(THREADS)
+sw_sim_generic(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
+{
+    __shared__ double red[2][THREADS / 32];
+    const int tid = threadIdx.x;
+    const int iN = g.iN, nF = g.iFactors;
+    const long long draws = (long long)(iN - 1) * nF;
+
+    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const int sw = item / g.chunks, chunk = item - sw * g.chunks;
+        const SwParams &P = params[sw];
+        __syncthreads();
+        double sum = 0.0, sumsq = 0.0;
+        for (int m = 0; m < g.tpt; ++m) {
+            const long long t = (long long)chunk * g.chunk_trials + (long long)m * THREADS + tid;
+            if (t >= P.sims) break;
+            long long ctr = P.seed + t * draws;
+            double row[MAXN], srow[MAXN], z[MAXF];
+            for (int l = 0; l < iN; ++l) {
+                row[l] = P.fwd[l];
+                srow[l] = row[l];
+            }
+            double run = 1.0, pay_df = 1.0;
+            for (int j = 1; j <= iN - 1; ++j) {
+                run = mul_rn(run, exp(mul_rn(-row[0], P.ddelt)));
+                if (j == P.start) pay_df = run;
+                for (int i = 0; i < nF; ++i) z[i] = cumnormalinv_ieee(ranunif_literal(ctr++));
+                for (int l = 0; l <= iN - 1 - j; ++l) {
+                    double shock = 0.0;
+                    for (int i = 0; i < nF; ++i) shock = add_rn(shock, mul_rn(P.fac[i][l], z[i]));
+                    row[l] = add_rn(add_rn(row[l + 1], P.driftdt[l]), mul_rn(P.sqrt_ddelt, shock));
+                }
+                row[iN - j] = 0.0;
+                if (j == P.start)
+                    for (int l = 0; l < iN; ++l) srow[l] = row[l];
+            }
+            double df = 1.0, fixed = 0.0;
+            for (int i = 0; i <= P.len - 1; ++i) {
+                if (i >= 1) df = mul_rn(df, exp(mul_rn(-srow[i - 1], P.swap_ddelt)));
+                fixed = add_rn(fixed, mul_rn(P.pay[i], df));
+            }
+            const double fm1 = add_rn(fixed, -1.0);
+            const double payoff = fm1 > 0.0 ? fm1 : 0.0;
+            const double disc = mul_rn(payoff, pay_df);
+            sum = add_rn(sum, disc);
+            sumsq = add_rn(sumsq, mul_rn(disc, disc));
+        }
+        block_sum2(sum, sumsq, red);
+        if (tid == 0) partials[item] = make_double2(sum, sumsq);
+    }
+}
+
+// One CTA per swaption: add its partials in a fixed order, then HSB:212-214.
+__global__ void __launch_bounds__(THREADS)
+sw_finalize(const SwParams *__restrict__ params, const Geom g, const double2 *__restrict__ partials,
+            double *__restrict__ mean, double *__restrict__ err)
+{
+    __shared__ double red[2][THREADS / 32];
+    const int sw = blockIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int c = threadIdx.x; c < g.chunks; c += THREADS) {
+        const double2 p = partials[(size_t)sw * g.chunks + c];
+        a += p.x;
+        b += p.y;
+    }
+    block_sum2(a, b, red);
+    if (threadIdx.x == 0) {
+        const double n = (double)params[sw].trials;
+        mean[sw] = __ddiv_rn(a, n);
+        const double var = __ddiv_rn(__dadd_rn(b, -__ddiv_rn(__dmul_rn(a, a), n)), __dadd_rn(n, -1.0));
+        err[sw] = __ddiv_rn(__dsqrt_rn(var), __dsqrt_rn(n));
+    }
+}
+
+}  // namespace swk

@@ -13,7 +13,9 @@ def _ensure_built():
     checker once, exactly as __graft_entry__.build() does.  Nothing is built when the files are already there."""
     import subprocess
     need = [os.path.join(ROOT, "p3arsec_b200", "lib", "libbs_gpu.so"), os.path.join(ROOT, "p3arsec_b200", "bin", "blackscholes_gpu"),
-            os.path.join(ROOT, "p3arsec_b200", "bin", "bs_inputgen"), os.path.join(ROOT, "oracle", "libbs_oracle.so")]
+            os.path.join(ROOT, "p3arsec_b200", "bin", "bs_inputgen"), os.path.join(ROOT, "oracle", "libbs_oracle.so"),
+            os.path.join(ROOT, "p3arsec_b200", "lib", "libsw_gpu.so"), os.path.join(ROOT, "p3arsec_b200", "bin", "swaptions_gpu"),
+            os.path.join(ROOT, "oracle", "libsw_oracle.so")]
     if all(os.path.exists(p) for p in need):
         return
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "p3arsec_b200", "csrc"), "-j4", "all"], check=True)
