@@ -3,7 +3,7 @@
  *
  * Reference body: parsec-ff/pkgs/apps/swaptions/src/HJM_Swaption_Blocking.cpp:20-222 (cited as HSB: below) and the
  * PARSEC-owned leaves it calls (RanUnif, CumNormalInv, HJM_SimPath_Forward_Blocking, Discount_Factors_Blocking;
- * absent from the overlay, semantics as restated in oracle/sw_absent/).
+ * absent from the P3ARSEC overlay: their published PARSEC 3.0 semantics are followed).
  *
  * Work decomposition.  A trial is independent of every other trial: RanUnif's state is a counter and draw k is a
  * pure function of (seed + k), so trial t of a swaption reads draws [30 t, 30 t + 30) (iN = 11, iFactors = 3).
@@ -88,12 +88,11 @@ __device__ __forceinline__ uint32_t ru_next(uint32_t x)
     x += 1513517u;
     return x >= RU_M ? x - RU_M : x;
 }
-__device__ __forceinline__ double ru_draw(uint32_t x)
+__device__ __forceinline__ uint32_t ru_int(uint32_t x)  // the 31-bit integer of the draw; u = ru_int * 4.656612875e-10
 {
     uint64_t p = (uint64_t)x * 16807ull;  // < 2^46
     uint32_t s = (uint32_t)(p & RU_M) + (uint32_t)(p >> 31);
-    s = s >= RU_M ? s - RU_M : s;
-    return (double)(int)s * 4.656612875e-10;
+    return s >= RU_M ? s - RU_M : s;
 }
 
 // Moro's coefficients; deliberately not const (see bs_tables_f64.h: const __constant__ doubles come back as
@@ -128,14 +127,39 @@ __device__ __noinline__ double cumnormalinv_ieee(double u)
     return x < 0.0 ? -p : p;
 }
 
-// exp for the fast kernel: the table-driven block for every argument the simulation can produce, libdevice for the
-// rest (|x| >= 700, inf, NaN -- reached only after a draw of exactly 0, see the tail below).
+// exp for the fast kernel.  exp_core = bsm::exp_f64 without its underflow clamp (11 FP64 operations), valid for
+// |x| < 700; everything else (huge rates, inf, NaN -- reached only after a draw of exactly 0, see the tail pass) goes
+// to libdevice, out of line.  The range check is done on the high word with integer instructions: the FP64 pipe is
+// the bottleneck of this kernel and a DSETP would cost it two issue cycles per exponential.
 __device__ __noinline__ double exp_slow(double x) { return exp(x); }
+__device__ __forceinline__ double exp_core(double x, const double *tab)
+{
+    using namespace bsm;
+    const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+    double nd = fma(x, kd(K_EXP_INV), MAGIC);
+    const int n = (int)(uint32_t)to_bits(nd);  // round(x * 64/ln2) = 64 k + j
+    nd -= MAGIC;
+    double r = fma(nd, -kd(K_EXP_HI), x);
+    r = fma(nd, -kd(K_EXP_LO), r);
+    double q = fma(kd(K_EXP_C5), r, kd(K_EXP_C4));
+    q = fma(q, r, kd(K_EXP_C3));
+    q = fma(q, r, 0.5);
+    const double em1 = fma(q, r * r, r);
+    const double T = tab[TAB_EXP + (n & 63)];
+    const double m = fma(T, em1, T);
+    return from_bits(to_bits(m) + ((uint64_t)(int64_t)(n >> 6) << 52));
+}
 __device__ __forceinline__ double exp_guarded(double x, const double *tab)
 {
-    if (!(fabs(x) < 700.0)) return exp_slow(x);
-    return bsm::exp_f64(x, tab);
+    const uint32_t hi = (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu;
+    if (hi >= 0x4085E000u) return exp_slow(x);  // |x| >= 700, inf, NaN
+    return exp_core(x, tab);
 }
+
+// CumNormalInv takes its central branch iff fabs(u - 0.5) < 0.42 with u = s * 4.656612875e-10 (s the 31-bit draw).
+// Both roundings are monotone in s, so the test is an integer range check: central <=> S_LO <= s <= S_HI
+// (found by bisection over the double arithmetic and verified around both edges by tests/test_sw_oracle.py).
+constexpr uint32_t S_LO = 171798692u, S_HI = 1975684955u;
 
 // Block-wide sum of two doubles; result valid in thread 0.
 __device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[THREADS / 32])
@@ -169,10 +193,9 @@ constexpr int FN = 11, FF = 3, FD = (FN - 1) * FF;
 
 struct FastShared {
     double tab[bsm::TAB_DOUBLES];
-    double z[FD][THREADS];
+    double z[FD][THREADS];     // the trial's normals, [draw][thread]: conflict-free, 240 B per thread
+    double4 fd[FN - 1];        // per maturity l: {fac0, fac1, fac2} * sqrt_ddelt and pdTotalDrift[l] * ddelt (two LDS.128)
     double fwd[FN];
-    double driftdt[FN - 1];
-    double fac[FF][FN - 1];  // pre-multiplied by sqrt_ddelt
     double pay[FN];
     double red[2][THREADS / 32];
 };
@@ -200,10 +223,10 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
                 sh.fwd[tid] = P.fwd[tid];
                 sh.pay[tid] = P.pay[tid];
             }
-            if (tid < FN - 1) sh.driftdt[tid] = P.driftdt[tid];
-            if (tid >= 32 && tid < 32 + FF * (FN - 1)) {
-                const int k = tid - 32, i = k / (FN - 1), l = k - i * (FN - 1);
-                sh.fac[i][l] = P.fac[i][l] * P.sqrt_ddelt;
+            if (tid >= 32 && tid < 32 + FN - 1) {
+                const int l = tid - 32;
+                const double sq = P.sqrt_ddelt;
+                sh.fd[l] = make_double4(P.fac[0][l] * sq, P.fac[1][l] * sq, P.fac[2][l] * sq, P.driftdt[l]);
             }
             ddelt = P.ddelt;
             swap_ddelt = P.swap_ddelt;
@@ -216,56 +239,59 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
         }
         __syncthreads();
 
-        const int steps = LEAN ? start : FN - 1;             // time steps whose shocks are needed
-        const int swap_end = LEAN ? last_pay : len - 1;      // last swap discount factor needed
+        const int steps = LEAN ? start : FN - 1;         // time steps whose shocks are needed
+        const int swap_end = LEAN ? last_pay : len - 1;  // last swap discount factor needed
         double sum = 0.0, sumsq = 0.0;
 
         for (int m = 0; m < g.tpt; ++m) {
             const long long t = (long long)chunk * g.chunk_trials + (long long)m * THREADS + tid;
             if (t >= sims) break;
 
-            // ---- phase A: the trial's normals.  Central branch for every draw; tail draws are noted in a mask and
-            // redone afterwards, so a warp pays for max-over-lanes(#tail draws) tail evaluations, not for 30.
-            uint32_t x = ru_residue(seed + t * FD);
-            uint32_t tail = 0;
-            const int ndraw = steps * FF;
-            for (int k = 0; k < ndraw; ++k) {
-                const double u = ru_draw(x);
-                x = ru_next(x);
-                const double xc = u - 0.5;
-                const double r = xc * xc;
-                double num = fma(MORO_A[3], r, MORO_A[2]);
-                num = fma(num, r, MORO_A[1]);
-                num = fma(num, r, MORO_A[0]);
-                double den = fma(MORO_B[3], r, MORO_B[2]);
-                den = fma(den, r, MORO_B[1]);
-                den = fma(den, r, MORO_B[0]);
-                den = fma(den, r, 1.0);
-                // tail draws (|xc| >= 0.42): keep u itself in the slot (the value the tail pass needs) and note the slot
-                const bool is_tail = !(fabs(xc) < 0.42);
-                const double zc = (xc * num) * bsm::rcp_f64(is_tail ? 1.0 : den);
-                sh.z[k][tid] = is_tail ? u : zc;
-                tail |= (is_tail ? 1u : 0u) << k;
+            // ---- phase A: the trial's normals through the central branch of CumNormalInv, three draws (one time step)
+            // at a time so that independent Horner chains overlap.  Draws that belong to the tail branch are noted in a
+            // mask and redone below: a warp then pays for max-over-lanes(#tail draws) tail evaluations, not for 30.
+            const uint32_t x0 = ru_residue(seed + t * FD);
+            uint32_t x = x0, tail = 0;
+#pragma unroll 2
+            for (int j = 0; j < steps; ++j) {
+#pragma unroll
+                for (int i = 0; i < FF; ++i) {
+                    const uint32_t s = ru_int(x);
+                    x = ru_next(x);
+                    const double u = (double)(int)s * 4.656612875e-10;
+                    const double xc = u - 0.5;
+                    const double r = xc * xc;
+                    double num = fma(MORO_A[3], r, MORO_A[2]);
+                    double den = fma(MORO_B[3], r, MORO_B[2]);
+                    num = fma(num, r, MORO_A[1]);
+                    den = fma(den, r, MORO_B[1]);
+                    num = fma(num, r, MORO_A[0]);
+                    den = fma(den, r, MORO_B[0]);
+                    den = fma(den, r, 1.0);
+                    sh.z[FF * j + i][tid] = (xc * num) * bsm::rcp_f64(den);  // garbage for tail draws: overwritten below
+                    tail |= (uint32_t)((s - S_LO) > (S_HI - S_LO)) << (FF * j + i);
+                }
             }
             while (tail) {
                 const int k = __ffs(tail) - 1;
                 tail &= tail - 1;
-                const double u = sh.z[k][tid];
-                const bool upper = u > 0.5;
-                double r = upper ? 1.0 - u : u;
-                double zt;
-                if (r > 0.0) {
-                    r = bsm::log_f64(-bsm::log_f64(r, sh.tab), sh.tab);
-                    double p = fma(r, MORO_C[8], MORO_C[7]);
-                    p = fma(r, p, MORO_C[6]);
-                    p = fma(r, p, MORO_C[5]);
-                    p = fma(r, p, MORO_C[4]);
-                    p = fma(r, p, MORO_C[3]);
-                    p = fma(r, p, MORO_C[2]);
-                    p = fma(r, p, MORO_C[1]);
-                    zt = fma(r, p, MORO_C[0]);
-                } else {
-                    zt = INFINITY;  // u == 0 (counter a multiple of 2^31 - 1): log(-log(0)) = +inf in the reference
+                uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
+                xk = xk >= RU_M ? xk - RU_M : xk;
+                const uint32_t s = ru_int(xk);
+                const double u = (double)(int)s * 4.656612875e-10;
+                const bool upper = s > S_HI;
+                const double r = upper ? 1.0 - u : u;
+                double zt = INFINITY;  // s == 0 (counter a multiple of 2^31 - 1): log(-log(0)) = +inf in the reference
+                if (s != 0) {
+                    const double w = bsm::log_f64(-bsm::log_f64(r, sh.tab), sh.tab);
+                    double p = fma(w, MORO_C[8], MORO_C[7]);
+                    p = fma(w, p, MORO_C[6]);
+                    p = fma(w, p, MORO_C[5]);
+                    p = fma(w, p, MORO_C[4]);
+                    p = fma(w, p, MORO_C[3]);
+                    p = fma(w, p, MORO_C[2]);
+                    p = fma(w, p, MORO_C[1]);
+                    zt = fma(w, p, MORO_C[0]);
                 }
                 sh.z[k][tid] = upper ? zt : -zt;
             }
@@ -281,20 +307,19 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             double run = 1.0, pay_df = 1.0;
 #pragma unroll
             for (int j = 1; j <= FN - 1; ++j) {
-                if (j <= steps || !LEAN) {
-                    if (!LEAN || j <= start) {
-                        run *= exp_guarded(-row[0] * ddelt, sh.tab);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
-                        if (j == start) pay_df = run;
-                    }
+                if (!LEAN || j <= steps) {
+                    run *= exp_guarded(-row[0] * ddelt, sh.tab);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
+                    if (j == start) pay_df = run;
                     const double z0 = sh.z[FF * (j - 1) + 0][tid];
                     const double z1 = sh.z[FF * (j - 1) + 1][tid];
                     const double z2 = sh.z[FF * (j - 1) + 2][tid];
 #pragma unroll
                     for (int l = 0; l <= FN - 1 - j; ++l) {
-                        double shock = sh.fac[0][l] * z0;
-                        shock = fma(sh.fac[1][l], z1, shock);
-                        shock = fma(sh.fac[2][l], z2, shock);
-                        row[l] = (row[l + 1] + sh.driftdt[l]) + shock;
+                        const double4 c = sh.fd[l];
+                        double shock = fma(c.x, z0, c.w);
+                        shock = fma(c.y, z1, shock);
+                        shock = fma(c.z, z2, shock);
+                        row[l] = row[l + 1] + shock;
                     }
                     row[FN - j] = 0.0;  // the reference's path matrix is zero beyond the triangle
                     if (j == start) {

@@ -3,10 +3,11 @@ outputs of the reference.
 
 Tolerance (BASELINE.json north_star: <= 1e-9 relative for fp64), written out:
   mean price   |d| <= 1e-9 |ref| + 1e-12
-  std error    |d| <= 1e-9 |ref| cond + 1e-12 with cond = max(1, mean^2 / (n stderr^2)): the reference forms the variance
-               as sumsq - sum^2/n (HJM_Swaption_Blocking.cpp:213), a cancellation that magnifies any difference in
-               the two sums (summation order included) by mean^2/variance.
-NaN / inf must sit where the reference has them.  The bound is loose on purpose: what the kernels actually reach is
+  std error    compared as the variance it is the root of: var = n stderr^2, |d var| <= 1e-9 (mean^2 + var) + 1e-24.
+               The reference forms var as sumsq - sum^2/n (HJM_Swaption_Blocking.cpp:213): a cancellation that
+               magnifies any difference in the two sums (summation order included) by mean^2/var, and that goes
+               negative -- std error NaN -- by rounding alone when every trial pays the same.
+NaN / inf prices must sit where the reference has them.  The bound is loose on purpose: what the kernels actually reach is
 printed by test_report_measured_distance and recorded in DESIGN.md.
 """
 import glob
@@ -32,18 +33,22 @@ MODES = [("fast", 0), ("lean", sw.FLAG_LEAN), ("ieee", sw.FLAG_IEEE), ("ieee_lea
 def assert_parity(mean, err, rmean, rerr, trials, what=""):
     mean, err, rmean, rerr = (np.asarray(a, np.float64) for a in (mean, err, rmean, rerr))
     assert np.array_equal(np.isnan(rmean), np.isnan(mean)), what + ": NaN prices differ"
-    assert np.array_equal(np.isnan(rerr), np.isnan(err)), what + ": NaN std errors differ\n%r\n%r" % (err, rerr)
     m = np.isfinite(rmean)
     assert np.array_equal(mean[~m & ~np.isnan(rmean)], rmean[~m & ~np.isnan(rmean)]), what + ": infinities differ"
     d = np.abs(mean[m] - rmean[m])
     assert (d <= 1e-9 * np.abs(rmean[m]) + 1e-12).all(), "%s: price off by %.3e (rel %.3e)" % (what, d.max(), (d / np.maximum(np.abs(rmean[m]), 1e-300)).max())
-    e = np.isfinite(rerr) & m
-    with np.errstate(divide="ignore", invalid="ignore"):
-        cond = np.where(rerr[e] > 0, np.maximum(1.0, rmean[e] ** 2 / (max(trials, 1) * rerr[e] ** 2)), 1.0)
-    de = np.abs(err[e] - rerr[e])
-    assert (de <= 1e-9 * np.abs(rerr[e]) * cond + 1e-12).all(), "%s: std error off by %.3e" % (what, de.max())
-    rel = float((d / np.maximum(np.abs(rmean[m]), 1e-300)).max()) if d.size else 0.0
-    return rel
+    # std error, compared where it is formed: var = n stderr^2 = (sumsq - sum^2/n)/(n-1).  A NaN std error is the square
+    # root of a negative variance estimate (extra trials of a ragged last block, or plain rounding when every trial pays
+    # the same); it counts as var <= 0, so "NaN vs 0" and "NaN vs 1e-12" are agreements when the price is large.
+    n = max(trials, 1)
+    with np.errstate(invalid="ignore"):
+        var_g = np.where(np.isnan(err[m]), 0.0, n * err[m] ** 2)
+        var_r = np.where(np.isnan(rerr[m]), 0.0, n * rerr[m] ** 2)
+    fin = np.isfinite(var_r)
+    assert np.array_equal(np.isfinite(var_g), fin), what + ": infinite std errors differ"
+    dv = np.abs(var_g[fin] - var_r[fin])
+    assert (dv <= 1e-9 * (rmean[m][fin] ** 2 + var_r[fin]) + 1e-24).all(), "%s: variance off by %.3e" % (what, dv.max())
+    return float((d / np.maximum(np.abs(rmean[m]), 1e-300)).max()) if d.size else 0.0
 
 
 def gpu_price(p, y, f, seed, trials, flags=0, block_size=16, num_gpus=1, iN=11, iFactors=3, geometry=None):
@@ -66,9 +71,8 @@ def test_reference_command_lines_match_committed_reference_output(name, mode, fl
     rmean = np.array([float(x[1]) for x in ref])
     rerr = np.array([float(x[2]) for x in ref])
     # the committed lines carry 10 decimals: compare at that resolution, then tighter against the oracle
-    assert np.array_equal(np.isnan(rerr), np.isnan(err))
     assert np.nanmax(np.abs(mean - rmean)) <= 0.5e-10 + 1e-9 * np.abs(rmean).max()
-    ok = ~np.isnan(rerr)
+    ok = ~np.isnan(rerr) & ~np.isnan(err)
     if ok.any():
         assert np.abs(err[ok] - rerr[ok]).max() <= 1e-9
     omean, oerr = so.price_map(p, y, f, seed, a["sm"])
@@ -249,7 +253,7 @@ def test_report_measured_distance(capsys):
         for mode, flags in MODES:
             mean, err, tm, _ = gpu_price(p, y, f, seed, 20000, flags)
             rel = assert_parity(mean, err, omean, oerr, 20000, mode)
-            ok = oerr > 0
+            ok = (oerr > 0) & np.isfinite(err)
             print("\n[sw parity] %-9s 32 x 20000: max rel |d price| = %.3e, max rel |d stderr| = %.3e, bit-identical prices %d/32, kernels %.3f ms"
                   % (mode, rel, float((np.abs(err[ok] - oerr[ok]) / oerr[ok]).max()), int((mean == omean).sum()), tm["roi_ms"]), end="")
         print()
