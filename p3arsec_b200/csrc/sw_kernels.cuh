@@ -149,10 +149,13 @@ __device__ __forceinline__ double exp_core(double x, const double *tab)
     const double m = fma(T, em1, T);
     return from_bits(to_bits(m) + ((uint64_t)(int64_t)(n >> 6) << 52));
 }
-__device__ __forceinline__ double exp_guarded(double x, const double *tab)
+// |x| >= 700, inf or NaN <=> (high word of x, sign cleared) >= EXP_HI_LIMIT.  The fast kernel evaluates every
+// exponential with exp_core, branch-free, and only tracks the largest such high word of the trial (LOP3 + VIMNMX on the
+// integer pipes); a trial that exceeded the limit is redone by generic_trial().
+constexpr uint32_t EXP_HI_LIMIT = 0x4085E000u;
+__device__ __forceinline__ double exp_tracked(double x, const double *tab, uint32_t &worst)
 {
-    const uint32_t hi = (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu;
-    if (hi >= 0x4085E000u) return exp_slow(x);  // |x| >= 700, inf, NaN
+    worst = max(worst, (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu);
     return exp_core(x, tab);
 }
 
@@ -160,6 +163,30 @@ __device__ __forceinline__ double exp_guarded(double x, const double *tab)
 // Both roundings are monotone in s, so the test is an integer range check: central <=> S_LO <= s <= S_HI
 // (found by bisection over the double arithmetic and verified around both edges by tests/test_sw_oracle.py).
 constexpr uint32_t S_LO = 171798692u, S_HI = 1975684955u;
+
+// CumNormalInv's tail branch for draw k of the trial whose first residue is x0, branch-free so that two of them can
+// be interleaved: z = -/+ P8(log(-log(min(u, 1 - u)))).  A draw of exactly 0 (counter a multiple of 2^31 - 1) gives
+// log(-log(0)) = +inf in the reference, hence z = -inf.
+__device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *tab)
+{
+    uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
+    xk = xk >= RU_M ? xk - RU_M : xk;
+    const uint32_t s = ru_int(xk);
+    const double u = (double)(int)s * 4.656612875e-10;
+    const bool upper = s > S_HI;
+    const double r = upper ? 1.0 - u : u;
+    const double w = bsm::log_f64(-bsm::log_f64(r, tab), tab);
+    double p = fma(w, MORO_C[8], MORO_C[7]);
+    p = fma(w, p, MORO_C[6]);
+    p = fma(w, p, MORO_C[5]);
+    p = fma(w, p, MORO_C[4]);
+    p = fma(w, p, MORO_C[3]);
+    p = fma(w, p, MORO_C[2]);
+    p = fma(w, p, MORO_C[1]);
+    p = fma(w, p, MORO_C[0]);
+    p = s == 0 ? INFINITY : p;
+    return upper ? p : -p;
+}
 
 // Block-wide sum of two doubles; result valid in thread 0.
 __device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[THREADS / 32])
@@ -184,6 +211,44 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[T
             b += red[1][i];
         }
     }
+}
+
+// =====================================================================================================================
+// One trial in the reference's operation order: libdevice exp/log, IEEE divide, every operation rounded on its own
+// (no FMA contraction), any iN <= 32 and iFactors <= 8, path rows in local memory.  Body of sw_sim_generic and the
+// out-of-line fallback of sw_sim_fast for trials whose exponentials leave the range of its fast arithmetic.
+// Returns the discounted payoff of trial t (HSB:198).
+// =====================================================================================================================
+__device__ __noinline__ double generic_trial(const SwParams &P, int iN, int nF, long long t)
+{
+    long long ctr = P.seed + t * ((long long)(iN - 1) * nF);
+    double row[MAXN], srow[MAXN], z[MAXF];
+    for (int l = 0; l < iN; ++l) {
+        row[l] = P.fwd[l];
+        srow[l] = row[l];
+    }
+    double run = 1.0, pay_df = 1.0;
+    for (int j = 1; j <= iN - 1; ++j) {
+        run = mul_rn(run, exp(mul_rn(-row[0], P.ddelt)));
+        if (j == P.start) pay_df = run;
+        for (int i = 0; i < nF; ++i) z[i] = cumnormalinv_ieee(ranunif_literal(ctr++));
+        for (int l = 0; l <= iN - 1 - j; ++l) {
+            double shock = 0.0;
+            for (int i = 0; i < nF; ++i) shock = add_rn(shock, mul_rn(P.fac[i][l], z[i]));
+            row[l] = add_rn(add_rn(row[l + 1], P.driftdt[l]), mul_rn(P.sqrt_ddelt, shock));
+        }
+        row[iN - j] = 0.0;
+        if (j == P.start)
+            for (int l = 0; l < iN; ++l) srow[l] = row[l];
+    }
+    double df = 1.0, fixed = 0.0;
+    for (int i = 0; i <= P.len - 1; ++i) {
+        if (i >= 1) df = mul_rn(df, exp(mul_rn(-srow[i - 1], P.swap_ddelt)));
+        fixed = add_rn(fixed, mul_rn(P.pay[i], df));
+    }
+    const double fm1 = add_rn(fixed, -1.0);
+    const double payoff = fm1 > 0.0 ? fm1 : 0.0;   // dMax (HSB:196)
+    return mul_rn(payoff, pay_df);                 // HSB:198
 }
 
 // =====================================================================================================================
@@ -272,32 +337,22 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
                     tail |= (uint32_t)((s - S_LO) > (S_HI - S_LO)) << (FF * j + i);
                 }
             }
+            // two tail draws per trip: their dependency chains (two logarithms and a degree-8 Horner each) interleave
             while (tail) {
-                const int k = __ffs(tail) - 1;
+                const int k0 = __ffs(tail) - 1;
                 tail &= tail - 1;
-                uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
-                xk = xk >= RU_M ? xk - RU_M : xk;
-                const uint32_t s = ru_int(xk);
-                const double u = (double)(int)s * 4.656612875e-10;
-                const bool upper = s > S_HI;
-                const double r = upper ? 1.0 - u : u;
-                double zt = INFINITY;  // s == 0 (counter a multiple of 2^31 - 1): log(-log(0)) = +inf in the reference
-                if (s != 0) {
-                    const double w = bsm::log_f64(-bsm::log_f64(r, sh.tab), sh.tab);
-                    double p = fma(w, MORO_C[8], MORO_C[7]);
-                    p = fma(w, p, MORO_C[6]);
-                    p = fma(w, p, MORO_C[5]);
-                    p = fma(w, p, MORO_C[4]);
-                    p = fma(w, p, MORO_C[3]);
-                    p = fma(w, p, MORO_C[2]);
-                    p = fma(w, p, MORO_C[1]);
-                    zt = fma(w, p, MORO_C[0]);
-                }
-                sh.z[k][tid] = upper ? zt : -zt;
+                const int k1 = tail ? __ffs(tail) - 1 : k0;  // odd count: the last trip does k0 twice
+                tail &= tail - 1;                            // (0 & anything == 0)
+                const double za = tail_normal(x0, k0, sh.tab);
+                const double zb = tail_normal(x0, k1, sh.tab);
+                sh.z[k0][tid] = za;
+                sh.z[k1][tid] = zb;
             }
 
             // ---- phase B: the forward-rate path, row by row (HJM_SimPath_Forward_Blocking), with column 0 feeding the
-            // payoff discount factor (HSB:167-172) and row `start` kept for the swap leg (HSB:179-183)
+            // payoff discount factor (HSB:167-172) and row `start` kept for the swap leg (HSB:179-183).  Every
+            // exponential is evaluated branch-free; `worst` remembers whether one of them left the fast range.
+            uint32_t worst = 0;
             double row[FN], srow[FN];
 #pragma unroll
             for (int l = 0; l < FN; ++l) {
@@ -308,8 +363,8 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
 #pragma unroll
             for (int j = 1; j <= FN - 1; ++j) {
                 if (!LEAN || j <= steps) {
-                    run *= exp_guarded(-row[0] * ddelt, sh.tab);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
-                    if (j == start) pay_df = run;
+                    run *= exp_tracked(-row[0] * ddelt, sh.tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
+                    pay_df = j == start ? run : pay_df;
                     const double z0 = sh.z[FF * (j - 1) + 0][tid];
                     const double z1 = sh.z[FF * (j - 1) + 1][tid];
                     const double z2 = sh.z[FF * (j - 1) + 2][tid];
@@ -329,17 +384,20 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
                 }
             }
 
-            // ---- swap leg: DF[i] = prod_{k<i} exp(-srow[k] swap_ddelt); fixed leg = sum pay[i] DF[i] (HSB:184-195)
+            // ---- swap leg: DF[i] = prod_{k<i} exp(-srow[k] swap_ddelt); fixed leg = sum pay[i] DF[i] (HSB:184-195).
+            // pay[i] is zero beyond the last payment and srow is zero beyond the row's length, so the full kernel sums
+            // all ten terms without a branch (0 * finite = 0; a non-finite factor sends the trial to generic_trial).
             double df = 1.0, fixed = 0.0;
 #pragma unroll
             for (int i = 1; i <= FN - 1; ++i) {
-                if (i <= swap_end) {
-                    df *= exp_guarded(-srow[i - 1] * swap_ddelt, sh.tab);
+                if (!LEAN || i <= swap_end) {
+                    df *= exp_tracked(-srow[i - 1] * swap_ddelt, sh.tab, worst);
                     fixed = fma(sh.pay[i], df, fixed);
                 }
             }
             const double payoff = fixed - 1.0 > 0.0 ? fixed - 1.0 : 0.0;  // dMax (HSB:196)
-            const double disc = payoff * pay_df;                          // HSB:198
+            double disc = payoff * pay_df;                                // HSB:198
+            if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[sw], FN, FF, t);
             sum += disc;                                                  // HSB:203
             sumsq = fma(disc, disc, sumsq);                               // HSB:204
         }
@@ -350,17 +408,13 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
 }
 
 // =====================================================================================================================
-// sw_sim_generic: any iN <= 32, iFactors <= 8; libdevice exp/log, IEEE divide, every operation rounded on its own in
-// the reference's order.  One trial per thread at a time, path rows in local memory.
+// sw_sim_generic: any iN <= 32, iFactors <= 8, one generic_trial() per thread at a time.
 // =====================================================================================================================
 __global__ void __launch_bounds__(THREADS)
 sw_sim_generic(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
 {
     __shared__ double red[2][THREADS / 32];
     const int tid = threadIdx.x;
-    const int iN = g.iN, nF = g.iFactors;
-    const long long draws = (long long)(iN - 1) * nF;
-
     for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
         const int sw = item / g.chunks, chunk = item - sw * g.chunks;
         const SwParams &P = params[sw];
@@ -369,36 +423,9 @@ sw_sim_generic(const SwParams *__restrict__ params, const Geom g, double2 *__res
         for (int m = 0; m < g.tpt; ++m) {
             const long long t = (long long)chunk * g.chunk_trials + (long long)m * THREADS + tid;
             if (t >= P.sims) break;
-            long long ctr = P.seed + t * draws;
-            double row[MAXN], srow[MAXN], z[MAXF];
-            for (int l = 0; l < iN; ++l) {
-                row[l] = P.fwd[l];
-                srow[l] = row[l];
-            }
-            double run = 1.0, pay_df = 1.0;
-            for (int j = 1; j <= iN - 1; ++j) {
-                run = mul_rn(run, exp(mul_rn(-row[0], P.ddelt)));
-                if (j == P.start) pay_df = run;
-                for (int i = 0; i < nF; ++i) z[i] = cumnormalinv_ieee(ranunif_literal(ctr++));
-                for (int l = 0; l <= iN - 1 - j; ++l) {
-                    double shock = 0.0;
-                    for (int i = 0; i < nF; ++i) shock = add_rn(shock, mul_rn(P.fac[i][l], z[i]));
-                    row[l] = add_rn(add_rn(row[l + 1], P.driftdt[l]), mul_rn(P.sqrt_ddelt, shock));
-                }
-                row[iN - j] = 0.0;
-                if (j == P.start)
-                    for (int l = 0; l < iN; ++l) srow[l] = row[l];
-            }
-            double df = 1.0, fixed = 0.0;
-            for (int i = 0; i <= P.len - 1; ++i) {
-                if (i >= 1) df = mul_rn(df, exp(mul_rn(-srow[i - 1], P.swap_ddelt)));
-                fixed = add_rn(fixed, mul_rn(P.pay[i], df));
-            }
-            const double fm1 = add_rn(fixed, -1.0);
-            const double payoff = fm1 > 0.0 ? fm1 : 0.0;
-            const double disc = mul_rn(payoff, pay_df);
-            sum = add_rn(sum, disc);
-            sumsq = add_rn(sumsq, mul_rn(disc, disc));
+            const double disc = generic_trial(P, g.iN, g.iFactors, t);
+            sum = add_rn(sum, disc);                      // HSB:203
+            sumsq = add_rn(sumsq, mul_rn(disc, disc));    // HSB:204
         }
         block_sum2(sum, sumsq, red);
         if (tid == 0) partials[item] = make_double2(sum, sumsq);
