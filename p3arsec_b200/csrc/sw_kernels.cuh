@@ -315,16 +315,21 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             // ---- phase A: the trial's normals through the central branch of CumNormalInv, three draws (one time step)
             // at a time so that independent Horner chains overlap.  Draws that belong to the tail branch are noted in a
             // mask and redone below: a warp then pays for max-over-lanes(#tail draws) tail evaluations, not for 30.
+            // The phase needs no exact residues: x0 + k c is left unreduced (< 2^31 + 2^26, so x * 16807 < 2^47 and the
+            // fold still gives a value congruent to the draw) and so is the folded sum, s in [0, 2^31 - 1 + 2^16): an
+            // unreduced s >= 2^31 - 1 stands for a draw below 2^16, i.e. a tail draw, fails the range check like one
+            // and is recomputed exactly by the tail pass.
             const uint32_t x0 = ru_residue(seed + t * FD);
-            uint32_t x = x0, tail = 0;
-#pragma unroll 2
-            for (int j = 0; j < steps; ++j) {
+            uint32_t tail = 0;
+#pragma unroll
+            for (int j = 0; j < FN - 1; ++j) {
+                if (LEAN && j >= steps) break;
 #pragma unroll
                 for (int i = 0; i < FF; ++i) {
-                    const uint32_t s = ru_int(x);
-                    x = ru_next(x);
-                    const double u = (double)(int)s * 4.656612875e-10;
-                    const double xc = u - 0.5;
+                    const int k = FF * j + i;
+                    const uint64_t p = (uint64_t)(x0 + (uint32_t)k * 1513517u) * 16807ull;
+                    const uint32_t s = (uint32_t)(p & RU_M) + (uint32_t)(p >> 31);
+                    const double xc = fma((double)(int)s, 4.656612875e-10, -0.5);  // u - 0.5 with one rounding instead of two
                     const double r = xc * xc;
                     double num = fma(MORO_A[3], r, MORO_A[2]);
                     double den = fma(MORO_B[3], r, MORO_B[2]);
@@ -333,8 +338,8 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
                     num = fma(num, r, MORO_A[0]);
                     den = fma(den, r, MORO_B[0]);
                     den = fma(den, r, 1.0);
-                    sh.z[FF * j + i][tid] = (xc * num) * bsm::rcp_f64(den);  // garbage for tail draws: overwritten below
-                    tail |= (uint32_t)((s - S_LO) > (S_HI - S_LO)) << (FF * j + i);
+                    sh.z[k][tid] = (xc * num) * bsm::rcp_f64(den);  // garbage for tail draws: overwritten below
+                    if ((s - S_LO) > (S_HI - S_LO)) tail |= 1u << k;
                 }
             }
             // two tail draws per trip: their dependency chains (two logarithms and a degree-8 Horner each) interleave
