@@ -265,8 +265,9 @@ struct FastShared {
     double red[2][THREADS / 32];
 };
 
-template <bool LEAN>
-__global__ void __launch_bounds__(THREADS, 4)
+// MINB = resident CTAs per SM the register allocation is bounded for (4: 128 registers, 5: 96, 6: 80).
+template <bool LEAN, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

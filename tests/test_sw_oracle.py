@@ -107,3 +107,55 @@ def test_invalid_time_indices_are_refused():
     p["dMaturity"] = 50.0      # swap start beyond the path
     with pytest.raises(ValueError):
         so.price_map(p, y, f, s, 16)
+
+
+# ---- host-checkable pieces of the device arithmetic (p3arsec_b200/csrc/sw_kernels.cuh) -------------------------------
+def _kernel_constants():
+    import re
+    src = open(os.path.join(os.path.dirname(GOLDEN), "..", "p3arsec_b200", "csrc", "sw_kernels.cuh")).read()
+    m = re.search(r"constexpr uint32_t S_LO = (\d+)u, S_HI = (\d+)u;", src)
+    return int(m.group(1)), int(m.group(2))
+
+
+def test_central_branch_integer_range_equals_the_double_test():
+    """The kernel decides CumNormalInv's branch with S_LO <= s <= S_HI on the 31-bit draw s; the reference decides it
+    with fabs(s * 4.656612875e-10 - 0.5) < 0.42 in doubles (two roundings).  Same decision for every s."""
+    s_lo, s_hi = _kernel_constants()
+    c = 4.656612875e-10
+
+    def central(s):
+        return abs(s * c - 0.5) < 0.42
+
+    for edge in (s_lo, s_hi):
+        for s in range(edge - 5000, edge + 5000):
+            assert central(s) == (s_lo <= s <= s_hi), s
+    rng = np.random.RandomState(3)
+    for s in rng.randint(0, 2**31 - 1, 20000):
+        assert central(int(s)) == (s_lo <= int(s) <= s_hi)
+    assert not central(0) and not central(2**31 - 2) and central(2**30)
+
+
+def test_residue_arithmetic_equals_ranunif():
+    """The kernel keeps x = ctr * 1513517 mod (2^31 - 1) as a 32-bit residue and computes 16807 x mod (2^31 - 1) with a
+    Mersenne fold instead of Schrage's split; phase A even leaves x and the folded sum unreduced.  Same draws."""
+    M = 2**31 - 1
+
+    def fold(p):
+        return (p & M) + (p >> 31)
+
+    rng = np.random.RandomState(5)
+    ctrs = [0, 1, M - 1, M, M + 1, 2 * M, 2**40 - 1] + [int(v) for v in rng.randint(0, 2**40, 3000, dtype=np.int64)]
+    for ctr in ctrs:
+        x = fold(fold(ctr * 1513517))
+        x = x - M if x >= M else x
+        assert x == (ctr * 1513517) % M
+        for k in (0, 1, 29):
+            xu = x + k * 1513517                       # unreduced, as in phase A
+            assert xu < 2**32
+            s = fold(xu * 16807)
+            true_s = int(round(so.ran_unif(ctr + k)[0] / 4.656612875e-10))
+            assert so.ran_unif(ctr + k)[0] == true_s * 4.656612875e-10
+            assert s % M == true_s and s < M + 2**16
+            if s != true_s:                            # unreduced sum: stands for a tiny draw and must fail the range check
+                s_lo, s_hi = _kernel_constants()
+                assert s > s_hi and true_s < s_lo

@@ -44,12 +44,13 @@ CPU_SAMPLE_TRIALS = 20_000  # per swaption, for the CPU reference
 FP64_LANES_PER_SM = 64
 
 
-def fp64_inst_per_trial(mode):
-    """FP64-pipe thread-instructions per trial, from the committed ncu capture (profiles/sw_ncu_counts.json)."""
+def ncu_counts():
+    """profiles/sw_ncu_counts.json: FP64-pipe thread-instructions per trial of each kernel flavour (from the committed
+    ncu captures) and the DFMA rate a pure-DFMA microbenchmark reaches on this pool's B200s."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "sw_ncu_counts.json")))[mode]
+        return json.load(open(os.path.join(ROOT, "profiles", "sw_ncu_counts.json")))
     except Exception:
-        return None
+        return {}
 
 
 def run_cpu_reference(ns, trials, steps, warmup):
@@ -176,15 +177,19 @@ def ours(args):
             spot = "unchecked: %s" % e
 
     # roofline: FP64 pipe
-    ipt = fp64_inst_per_trial(args.mode)
+    counts = ncu_counts()
+    ipt = counts.get(args.mode)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965
     props = torch.cuda.get_device_properties(local_rank)
-    peak = props.multi_processor_count * FP64_LANES_PER_SM * sm_mhz * 1e6 / 1e12  # T FP64-pipe thread-instructions / s
+    nominal = props.multi_processor_count * FP64_LANES_PER_SM * sm_mhz * 1e6 / 1e12  # T FP64-pipe thread-instructions / s
+    peak = counts.get("fp64_peak_measured_tinst_per_s") or nominal
     per_gpu_rate = (sims_local / max(in_process_gpus, 1)) / (dev_ms * 1e-3)
     achieved = (ipt * per_gpu_rate / 1e12) if ipt else None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "T fp64-pipe thread-instructions/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "peak_source": "%d SMs x %d FP64 lanes x %d MHz (clock sampled during the run)" % (props.multi_processor_count, FP64_LANES_PER_SM, sm_mhz),
+                "peak_source": counts.get("fp64_peak_source") or "nominal",
+                "nominal_peak": nominal, "frac_of_nominal": (achieved / nominal) if achieved else None,
+                "nominal_source": "%d SMs x %d FP64 lanes x %d MHz (clock sampled during the run)" % (props.multi_processor_count, FP64_LANES_PER_SM, sm_mhz),
                 "kernel": "swk::sw_sim_fast<%s>" % ("true" if args.mode == "lean" else "false") if args.mode != "ieee" else "swk::sw_sim_generic",
                 "fp64_pipe_instructions_per_trial": ipt, "trials_per_launch": int(sims_local / args.steps / max(in_process_gpus, 1)),
                 "avg_launch_us": dev_ms / args.steps * 1e3,
