@@ -265,6 +265,141 @@ struct FastShared {
     double red[2][THREADS / 32];
 };
 
+// ---- phase A + tail pass -----------------------------------------------------------------------------------------------
+// The trial's normals into sh.z[draw][tid].  Central branch of CumNormalInv for every draw, G draws at a time written stage
+// by stage so that G independent Horner chains are in flight (the FP64 pipe has a long dependent-issue latency and only
+// four warps per scheduler to hide it).  Draws that belong to the tail branch are noted in a mask and redone afterwards,
+// three per trip: a warp pays for max-over-lanes(#tail draws) tail evaluations, not for 30.
+// The phase needs no exact residues: x0 + k c is left unreduced (< 2^31 + 2^26, so x * 16807 < 2^47 and the fold still
+// gives a value congruent to the draw) and so is the folded sum, s in [0, 2^31 - 1 + 2^16): an unreduced s >= 2^31 - 1
+// stands for a draw below 2^16, i.e. a tail draw, fails the range check like one and is recomputed exactly by the tail pass.
+template <bool LEAN>
+__device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, int steps)
+{
+    constexpr int G = LEAN ? FF : 2 * FF;
+    uint32_t tail = 0;
+#pragma unroll
+    for (int k0 = 0; k0 < FD; k0 += G) {
+        if (LEAN && k0 >= FF * steps) break;
+        uint32_t sg[G];
+        double xc[G], r[G], num[G], den[G], q[G], rx[G], e[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const uint64_t p = (uint64_t)(x0 + (uint32_t)(k0 + i) * 1513517u) * 16807ull;
+            sg[i] = (uint32_t)(p & RU_M) + (uint32_t)(p >> 31);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) xc[i] = fma((double)(int)sg[i], 4.656612875e-10, -0.5);  // u - 0.5, one rounding
+#pragma unroll
+        for (int i = 0; i < G; ++i) r[i] = xc[i] * xc[i];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            num[i] = fma(MORO_A[3], r[i], MORO_A[2]);
+            den[i] = fma(MORO_B[3], r[i], MORO_B[2]);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            num[i] = fma(num[i], r[i], MORO_A[1]);
+            den[i] = fma(den[i], r[i], MORO_B[1]);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            num[i] = fma(num[i], r[i], MORO_A[0]);
+            den[i] = fma(den[i], r[i], MORO_B[0]);
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            den[i] = fma(den[i], r[i], 1.0);
+            q[i] = xc[i] * num[i];
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) rx[i] = bsm::seed_rcp(den[i]);       // MUFU.RCP64H
+#pragma unroll
+        for (int i = 0; i < G; ++i) e[i] = fma(-den[i], rx[i], 1.0);     // one cubic Newton step: x (1 + e + e^2)
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            e[i] = fma(e[i], e[i], e[i]);
+            q[i] = q[i] * rx[i];
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            sh.z[k0 + i][tid] = fma(q[i], e[i], q[i]);  // garbage for tail draws: overwritten below
+            if ((sg[i] - S_LO) > (S_HI - S_LO)) tail |= 1u << (k0 + i);
+        }
+    }
+    while (tail) {
+        const int k0 = __ffs(tail) - 1;
+        tail &= tail - 1;
+        const int k1 = tail ? __ffs(tail) - 1 : k0;  // fewer than three left: the last trip repeats a draw
+        tail &= tail - 1;                            // (0 & anything == 0)
+        const int k2 = tail ? __ffs(tail) - 1 : k0;
+        tail &= tail - 1;
+        const double za = tail_normal(x0, k0, sh.tab);
+        const double zb = tail_normal(x0, k1, sh.tab);
+        const double zc = tail_normal(x0, k2, sh.tab);
+        sh.z[k0][tid] = za;
+        sh.z[k1][tid] = zb;
+        sh.z[k2][tid] = zc;
+    }
+}
+
+// ---- phase B --------------------------------------------------------------------------------------------------------------
+// The forward-rate path row by row in registers (HJM_SimPath_Forward_Blocking), column 0 feeding the payoff discount
+// factor (HSB:167-172), row `start` feeding the swap leg (HSB:179-195); returns the discounted payoff (HSB:198).
+// START >= 0: the swap start index as a compile-time constant -- the row snapshot is then a register renaming and the
+// whole phase is one basic block; START < 0: taken from start_rt.  Every exponential is evaluated branch-free; `worst`
+// remembers whether one of them left the fast range.
+template <bool LEAN, int START>
+__device__ __forceinline__ double path_and_payoff(const FastShared &sh, int tid, double ddelt, double swap_ddelt, int start_rt,
+                                                  int swap_end, uint32_t &worst)
+{
+    const int start = START >= 0 ? START : start_rt;
+    const int steps = LEAN ? start : FN - 1;  // time steps whose shocks are needed
+    double row[FN], srow[FN];
+#pragma unroll
+    for (int l = 0; l < FN; ++l) {
+        row[l] = sh.fwd[l];
+        srow[l] = row[l];  // start == 0
+    }
+    double run = 1.0, pay_df = 1.0;
+#pragma unroll
+    for (int j = 1; j <= FN - 1; ++j) {
+        if (!LEAN || j <= steps) {
+            run *= exp_tracked(-row[0] * ddelt, sh.tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
+            const double z0 = sh.z[FF * (j - 1) + 0][tid];
+            const double z1 = sh.z[FF * (j - 1) + 1][tid];
+            const double z2 = sh.z[FF * (j - 1) + 2][tid];
+#pragma unroll
+            for (int l = 0; l <= FN - 1 - j; ++l) {
+                const double4 c = sh.fd[l];
+                double shock = fma(c.x, z0, c.w);
+                shock = fma(c.y, z1, shock);
+                shock = fma(c.z, z2, shock);
+                row[l] = row[l + 1] + shock;
+            }
+            row[FN - j] = 0.0;  // the reference's path matrix is zero beyond the triangle
+            if (j == start) {
+                pay_df = run;
+#pragma unroll
+                for (int l = 0; l < FN; ++l) srow[l] = row[l];
+            }
+        }
+    }
+    // swap leg: DF[i] = prod_{k<i} exp(-srow[k] swap_ddelt); fixed leg = sum pay[i] DF[i] (HSB:184-195).  pay[i] is zero
+    // beyond the last payment and srow is zero beyond the row's length, so the full kernel sums all ten terms without a
+    // branch (0 * finite = 0; a non-finite factor sends the trial to generic_trial).
+    double df = 1.0, fixed = 0.0;
+#pragma unroll
+    for (int i = 1; i <= FN - 1; ++i) {
+        if (!LEAN || i <= swap_end) {
+            df *= exp_tracked(-srow[i - 1] * swap_ddelt, sh.tab, worst);
+            fixed = fma(sh.pay[i], df, fixed);
+        }
+    }
+    const double payoff = fixed - 1.0 > 0.0 ? fixed - 1.0 : 0.0;  // dMax (HSB:196)
+    return payoff * pay_df;                                       // HSB:198
+}
+
 // MINB = resident CTAs per SM the register allocation is bounded for (4: 128 registers, 5: 96, 6: 80).
 template <bool LEAN, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -313,96 +448,19 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             const long long t = (long long)chunk * g.chunk_trials + (long long)m * THREADS + tid;
             if (t >= sims) break;
 
-            // ---- phase A: the trial's normals through the central branch of CumNormalInv, three draws (one time step)
-            // at a time so that independent Horner chains overlap.  Draws that belong to the tail branch are noted in a
-            // mask and redone below: a warp then pays for max-over-lanes(#tail draws) tail evaluations, not for 30.
-            // The phase needs no exact residues: x0 + k c is left unreduced (< 2^31 + 2^26, so x * 16807 < 2^47 and the
-            // fold still gives a value congruent to the draw) and so is the folded sum, s in [0, 2^31 - 1 + 2^16): an
-            // unreduced s >= 2^31 - 1 stands for a draw below 2^16, i.e. a tail draw, fails the range check like one
-            // and is recomputed exactly by the tail pass.
-            const uint32_t x0 = ru_residue(seed + t * FD);
-            uint32_t tail = 0;
-#pragma unroll
-            for (int j = 0; j < FN - 1; ++j) {
-                if (LEAN && j >= steps) break;
-#pragma unroll
-                for (int i = 0; i < FF; ++i) {
-                    const int k = FF * j + i;
-                    const uint64_t p = (uint64_t)(x0 + (uint32_t)k * 1513517u) * 16807ull;
-                    const uint32_t s = (uint32_t)(p & RU_M) + (uint32_t)(p >> 31);
-                    const double xc = fma((double)(int)s, 4.656612875e-10, -0.5);  // u - 0.5 with one rounding instead of two
-                    const double r = xc * xc;
-                    double num = fma(MORO_A[3], r, MORO_A[2]);
-                    double den = fma(MORO_B[3], r, MORO_B[2]);
-                    num = fma(num, r, MORO_A[1]);
-                    den = fma(den, r, MORO_B[1]);
-                    num = fma(num, r, MORO_A[0]);
-                    den = fma(den, r, MORO_B[0]);
-                    den = fma(den, r, 1.0);
-                    sh.z[k][tid] = (xc * num) * bsm::rcp_f64(den);  // garbage for tail draws: overwritten below
-                    if ((s - S_LO) > (S_HI - S_LO)) tail |= 1u << k;
-                }
-            }
-            // two tail draws per trip: their dependency chains (two logarithms and a degree-8 Horner each) interleave
-            while (tail) {
-                const int k0 = __ffs(tail) - 1;
-                tail &= tail - 1;
-                const int k1 = tail ? __ffs(tail) - 1 : k0;  // odd count: the last trip does k0 twice
-                tail &= tail - 1;                            // (0 & anything == 0)
-                const double za = tail_normal(x0, k0, sh.tab);
-                const double zb = tail_normal(x0, k1, sh.tab);
-                sh.z[k0][tid] = za;
-                sh.z[k1][tid] = zb;
-            }
+            // ---- phase A + tail pass: the trial's normals into sh.z (see normals())
+            normals<LEAN>(sh, tid, ru_residue(seed + t * FD), steps);
 
-            // ---- phase B: the forward-rate path, row by row (HJM_SimPath_Forward_Blocking), with column 0 feeding the
-            // payoff discount factor (HSB:167-172) and row `start` kept for the swap leg (HSB:179-183).  Every
-            // exponential is evaluated branch-free; `worst` remembers whether one of them left the fast range.
+            // ---- phase B: path, discount factors, payoff; specialised on the swap start index (1..3 covers every
+            // swaption the reference drivers create: dMaturity = 1, dYears in [5, 20))
             uint32_t worst = 0;
-            double row[FN], srow[FN];
-#pragma unroll
-            for (int l = 0; l < FN; ++l) {
-                row[l] = sh.fwd[l];
-                srow[l] = row[l];  // start == 0
+            double disc;
+            switch (start) {
+                case 1: disc = path_and_payoff<LEAN, 1>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 2: disc = path_and_payoff<LEAN, 2>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 3: disc = path_and_payoff<LEAN, 3>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                default: disc = path_and_payoff<LEAN, -1>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
             }
-            double run = 1.0, pay_df = 1.0;
-#pragma unroll
-            for (int j = 1; j <= FN - 1; ++j) {
-                if (!LEAN || j <= steps) {
-                    run *= exp_tracked(-row[0] * ddelt, sh.tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
-                    pay_df = j == start ? run : pay_df;
-                    const double z0 = sh.z[FF * (j - 1) + 0][tid];
-                    const double z1 = sh.z[FF * (j - 1) + 1][tid];
-                    const double z2 = sh.z[FF * (j - 1) + 2][tid];
-#pragma unroll
-                    for (int l = 0; l <= FN - 1 - j; ++l) {
-                        const double4 c = sh.fd[l];
-                        double shock = fma(c.x, z0, c.w);
-                        shock = fma(c.y, z1, shock);
-                        shock = fma(c.z, z2, shock);
-                        row[l] = row[l + 1] + shock;
-                    }
-                    row[FN - j] = 0.0;  // the reference's path matrix is zero beyond the triangle
-                    if (j == start) {
-#pragma unroll
-                        for (int l = 0; l < FN; ++l) srow[l] = row[l];
-                    }
-                }
-            }
-
-            // ---- swap leg: DF[i] = prod_{k<i} exp(-srow[k] swap_ddelt); fixed leg = sum pay[i] DF[i] (HSB:184-195).
-            // pay[i] is zero beyond the last payment and srow is zero beyond the row's length, so the full kernel sums
-            // all ten terms without a branch (0 * finite = 0; a non-finite factor sends the trial to generic_trial).
-            double df = 1.0, fixed = 0.0;
-#pragma unroll
-            for (int i = 1; i <= FN - 1; ++i) {
-                if (!LEAN || i <= swap_end) {
-                    df *= exp_tracked(-srow[i - 1] * swap_ddelt, sh.tab, worst);
-                    fixed = fma(sh.pay[i], df, fixed);
-                }
-            }
-            const double payoff = fixed - 1.0 > 0.0 ? fixed - 1.0 : 0.0;  // dMax (HSB:196)
-            double disc = payoff * pay_df;                                // HSB:198
             if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[sw], FN, FF, t);
             sum += disc;                                                  // HSB:203
             sumsq = fma(disc, disc, sumsq);                               // HSB:204
