@@ -33,8 +33,6 @@
 
 namespace {
 
-const int DEFAULT_MINB = 4;  // CTAs per SM the default fast kernel build is register-bounded for
-
 struct Dev {
     int device = 0;
     int sm_count = 0;
@@ -45,7 +43,7 @@ struct Dev {
     double2 *d_partials = nullptr;
     size_t partial_cap = 0;
     double *d_out = nullptr;  // [mean(max) | err(max)]
-    int occ_fast[3] = {0, 0, 0}, occ_lean[3] = {0, 0, 0}, occ_generic = 0;  // [MINB - 4]
+    int occ_fast = 0, occ_lean = 0, occ_generic = 0;
     float roi_ms = 0;
 };
 
@@ -148,15 +146,6 @@ bool prepare(swk::SwParams &P, const sw_gpu_swaption &s, int iN, int iFactors, c
 
 enum Kind { K_FAST = 0, K_LEAN = 1, K_GENERIC = 2 };
 
-typedef void (*FastKernel)(const swk::SwParams *, const swk::Geom, double2 *);
-// The fast kernel is built three times, its register allocation bounded for 4, 5 or 6 resident CTAs per SM.
-FastKernel fast_kernel(bool lean, int v)
-{
-    static const FastKernel full[3] = {swk::sw_sim_fast<false, 4>, swk::sw_sim_fast<false, 5>, swk::sw_sim_fast<false, 6>};
-    static const FastKernel ln[3] = {swk::sw_sim_fast<true, 4>, swk::sw_sim_fast<true, 5>, swk::sw_sim_fast<true, 6>};
-    return lean ? ln[v] : full[v];
-}
-
 }  // namespace
 
 extern "C" {
@@ -226,14 +215,12 @@ static int init_impl(sw_gpu_ctx *c, const int *devices, int num_gpus)
         SW_CUDA(c, cudaEventCreate(&d.ev1));
         SW_CUDA(c, cudaMalloc(&d.d_params, n * sizeof(swk::SwParams)));
         SW_CUDA(c, cudaMalloc(&d.d_out, 2 * n * sizeof(double)));
-        for (int v = 0; v < 3; ++v) {
-            SW_CUDA(c, cudaFuncSetAttribute(fast_kernel(false, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
-            SW_CUDA(c, cudaFuncSetAttribute(fast_kernel(true, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
-            SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fast[v], fast_kernel(false, v), swk::THREADS, sizeof(swk::FastShared)));
-            SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean[v], fast_kernel(true, v), swk::THREADS, sizeof(swk::FastShared)));
-        }
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fast, swk::sw_sim_fast<false>, swk::THREADS, sizeof(swk::FastShared)));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean, swk::sw_sim_fast<true>, swk::THREADS, sizeof(swk::FastShared)));
         SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_generic, swk::sw_sim_generic, swk::THREADS, 0));
-        if (d.occ_fast[0] < 1 || d.occ_lean[0] < 1 || d.occ_generic < 1) return fail(c, SW_GPU_ERR_CUDA, "a kernel does not fit on device %d", d.device);
+        if (d.occ_fast < 1 || d.occ_lean < 1 || d.occ_generic < 1) return fail(c, SW_GPU_ERR_CUDA, "a kernel does not fit on device %d", d.device);
     }
     SW_CUDA(c, cudaHostAlloc(&c->h_params, n * sizeof(swk::SwParams), cudaHostAllocPortable));
     SW_CUDA(c, cudaHostAlloc(&c->h_out, 2 * n * sizeof(double), cudaHostAllocPortable));
@@ -312,9 +299,7 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         d.count = q + (g < r ? 1 : 0);
         first += d.count;
 
-        // build variant: the one bounded for the requested CTAs per SM (default: DEFAULT_MINB)
-        const int v = std::max(0, std::min(2, (c->cfg_ctas_per_sm > 0 ? c->cfg_ctas_per_sm : DEFAULT_MINB) - 4));
-        const int occ = kind == K_FAST ? d.occ_fast[v] : kind == K_LEAN ? d.occ_lean[v] : d.occ_generic;
+        const int occ = kind == K_FAST ? d.occ_fast : kind == K_LEAN ? d.occ_lean : d.occ_generic;
         const int per_sm = c->cfg_ctas_per_sm > 0 ? std::min(c->cfg_ctas_per_sm, occ) : occ;
         const long long grid_threads = (long long)d.sm_count * per_sm * swk::THREADS;
         // trials per thread per item: enough items for ~8 per resident CTA (static round-robin balance), capped
@@ -344,8 +329,10 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         }
         SW_CUDA(c, cudaMemcpyAsync(d.d_params, c->h_params + d.first, (size_t)d.count * sizeof(swk::SwParams), cudaMemcpyHostToDevice, d.stream));
         SW_CUDA(c, cudaEventRecord(d.ev0, d.stream));
-        if (kind != K_GENERIC)
-            fast_kernel(kind == K_LEAN, v)<<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
+        if (kind == K_FAST)
+            swk::sw_sim_fast<false><<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
+        else if (kind == K_LEAN)
+            swk::sw_sim_fast<true><<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
         else
             swk::sw_sim_generic<<<blocks, swk::THREADS, 0, d.stream>>>(d.d_params, geo, d.d_partials);
         SW_CUDA(c, cudaGetLastError());

@@ -24,6 +24,7 @@
 #include <stdint.h>
 
 #include "bs_math_f64.h"
+#include "sw_tail.h"
 
 namespace swk {
 
@@ -164,10 +165,10 @@ __device__ __forceinline__ double exp_tracked(double x, const double *tab, uint3
 // (found by bisection over the double arithmetic and verified around both edges by tests/test_sw_oracle.py).
 constexpr uint32_t S_LO = 171798692u, S_HI = 1975684955u;
 
-// CumNormalInv's tail branch for draw k of the trial whose first residue is x0, branch-free so that two of them can
+// CumNormalInv's tail branch for draw k of the trial whose first residue is x0, branch-free so that several of them can
 // be interleaved: z = -/+ P8(log(-log(min(u, 1 - u)))).  A draw of exactly 0 (counter a multiple of 2^31 - 1) gives
 // log(-log(0)) = +inf in the reference, hence z = -inf.
-__device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *tab)
+__device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *tab, const double *tailtab)
 {
     uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
     xk = xk >= RU_M ? xk - RU_M : xk;
@@ -175,6 +176,7 @@ __device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *
     const double u = (double)(int)s * 4.656612875e-10;
     const bool upper = s > S_HI;
     const double r = upper ? 1.0 - u : u;
+#if defined(SW_TAIL_TWO_LOGS)
     const double w = bsm::log_f64(-bsm::log_f64(r, tab), tab);
     double p = fma(w, MORO_C[8], MORO_C[7]);
     p = fma(w, p, MORO_C[6]);
@@ -184,6 +186,9 @@ __device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *
     p = fma(w, p, MORO_C[2]);
     p = fma(w, p, MORO_C[1]);
     p = fma(w, p, MORO_C[0]);
+#else
+    double p = swt::moro_tail(r, tab, tailtab);  // P8(log(-log r)): one logarithm + the composite table (sw_tail.h)
+#endif
     p = s == 0 ? INFINITY : p;
     return upper ? p : -p;
 }
@@ -257,6 +262,7 @@ __device__ __noinline__ double generic_trial(const SwParams &P, int iN, int nF, 
 constexpr int FN = 11, FF = 3, FD = (FN - 1) * FF;
 
 struct FastShared {
+    double tail[swt::TAIL_DOUBLES];  // composite table of Moro's tail branch (5 KB; rows of 80 B, 16-byte aligned)
     double tab[bsm::TAB_DOUBLES];
     double z[FD][THREADS];     // the trial's normals, [draw][thread]: conflict-free, 240 B per thread
     double4 fd[FN - 1];        // per maturity l: {fac0, fac1, fac2} * sqrt_ddelt and pdTotalDrift[l] * ddelt (two LDS.128)
@@ -273,10 +279,21 @@ struct FastShared {
 // The phase needs no exact residues: x0 + k c is left unreduced (< 2^31 + 2^26, so x * 16807 < 2^47 and the fold still
 // gives a value congruent to the draw) and so is the folded sum, s in [0, 2^31 - 1 + 2^16): an unreduced s >= 2^31 - 1
 // stands for a draw below 2^16, i.e. a tail draw, fails the range check like one and is recomputed exactly by the tail pass.
+// Tuning knobs of the full kernel (measured on B200, 128 x 1M trials: every combination of 2/3/6 tail draws per trip,
+// 3/6/10 draws per phase-A group, row-/coefficient-major tail table or two logarithms lands within 11.0-11.3 G trials/s;
+// profiles/r01_sw_variants.txt).
+#ifndef SW_TAIL_TRIP
+#define SW_TAIL_TRIP 6
+#endif
+#ifndef SW_PHASE_A_GROUP
+#define SW_PHASE_A_GROUP 6  /* draws evaluated side by side in phase A: 3, 6, 10, 15 or 30 */
+#endif
+constexpr int TAIL_TRIP = SW_TAIL_TRIP;
+
 template <bool LEAN>
 __device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, int steps)
 {
-    constexpr int G = LEAN ? FF : 2 * FF;
+    constexpr int G = LEAN ? FF : SW_PHASE_A_GROUP;
     uint32_t tail = 0;
 #pragma unroll
     for (int k0 = 0; k0 < FD; k0 += G) {
@@ -330,16 +347,23 @@ __device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, in
     while (tail) {
         const int k0 = __ffs(tail) - 1;
         tail &= tail - 1;
-        const int k1 = tail ? __ffs(tail) - 1 : k0;  // fewer than three left: the last trip repeats a draw
-        tail &= tail - 1;                            // (0 & anything == 0)
-        const int k2 = tail ? __ffs(tail) - 1 : k0;
-        tail &= tail - 1;
-        const double za = tail_normal(x0, k0, sh.tab);
-        const double zb = tail_normal(x0, k1, sh.tab);
-        const double zc = tail_normal(x0, k2, sh.tab);
-        sh.z[k0][tid] = za;
-        sh.z[k1][tid] = zb;
-        sh.z[k2][tid] = zc;
+        if (LEAN) {  // three or six draws per trial: rarely more than one tail draw per lane
+            sh.z[k0][tid] = tail_normal(x0, k0, sh.tab, sh.tail);
+        } else {
+            // TRIP draws per trip with interleaved chains; with fewer left the last trip repeats draw k0
+            int kk[TAIL_TRIP];
+            double zz[TAIL_TRIP];
+            kk[0] = k0;
+#pragma unroll
+            for (int i = 1; i < TAIL_TRIP; ++i) {
+                kk[i] = tail ? __ffs(tail) - 1 : k0;
+                tail &= tail - 1;  // (0 & anything == 0)
+            }
+#pragma unroll
+            for (int i = 0; i < TAIL_TRIP; ++i) zz[i] = tail_normal(x0, kk[i], sh.tab, sh.tail);
+#pragma unroll
+            for (int i = 0; i < TAIL_TRIP; ++i) sh.z[kk[i]][tid] = zz[i];
+        }
     }
 }
 
@@ -400,15 +424,17 @@ __device__ __forceinline__ double path_and_payoff(const FastShared &sh, int tid,
     return payoff * pay_df;                                       // HSB:198
 }
 
-// MINB = resident CTAs per SM the register allocation is bounded for (4: 128 registers, 5: 96, 6: 80).
-template <bool LEAN, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
+// Four CTAs (16 warps) per SM: 128 registers per thread.  Builds bounded for 5 and 6 CTAs (96 / 80 registers) spill
+// the path rows and measured 4-12 % slower.
+template <bool LEAN>
+__global__ void __launch_bounds__(THREADS, 4)
 sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
     const int tid = threadIdx.x;
     bsm::fill_tables(sh.tab, tid, THREADS);
+    swt::fill_tail(sh.tail, tid, THREADS);
 
     int cur = -1;
     double ddelt = 0, swap_ddelt = 0;

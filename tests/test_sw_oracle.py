@@ -159,3 +159,14 @@ def test_residue_arithmetic_equals_ranunif():
             if s != true_s:                            # unreduced sum: stands for a tiny draw and must fail the range check
                 s_lo, s_hi = _kernel_constants()
                 assert s > s_hi and true_s < s_lo
+
+
+def test_tail_table_matches_long_double_libm(tmp_path):
+    """p3arsec_b200/csrc/sw_tail.h (host-or-device): one logarithm + the composite table against P8(log(-log r)) in
+    long double, over 4 M random tail draws and the 200 000 smallest draws exhaustively."""
+    import subprocess
+    root = os.path.join(os.path.dirname(GOLDEN), "..")
+    exe = str(tmp_path / "sw_tail_host_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tools", "sw_tail_host_check.cpp"), "-lm"], check=True)
+    out = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert float(out["max_rel"]) < 5e-16 and float(out["max_ulp"]) <= 2.5
