@@ -257,3 +257,26 @@ def test_report_measured_distance(capsys):
             print("\n[sw parity] %-9s 32 x 20000: max rel |d price| = %.3e, max rel |d stderr| = %.3e, bit-identical prices %d/32, kernels %.3f ms"
                   % (mode, rel, float((np.abs(err[ok] - oerr[ok]) / oerr[ok]).max()), int((mean == omean).sum()), tm["roi_ms"]), end="")
         print()
+
+
+def test_reference_driver_with_cuda_map():
+    """oracle/_ref/sw_ref_cuda = the reference's own HJM_Securities.cpp with integration/HJM_Securities.cpp.enable_cuda.patch
+    (its argument handling, RanUnif-driven portfolio set-up, ROI markers and result printing; only the Map is
+    sw_gpu_price) against the committed output of the unmodified CPU builds."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "sw_ref_cuda")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/sw_ref_cuda not built (needs /root/reference at build time)")
+    for name in ("simsmall16", "ragged7", "seeds5"):
+        gold = json.load(open(os.path.join(GOLDEN, "sw_%s.json" % name)))
+        a = gold["args"]
+        cmd = [exe, "-ns", str(a["ns"]), "-sm", str(a["sm"]), "-nt", "1"] + (["-sd", str(a["sd"])] if a["sd"] is not None else [])
+        cp = subprocess.run(cmd, capture_output=True, text=True)
+        assert cp.returncode == 0, cp.stderr
+        assert "roi.time|" in cp.stdout  # the hooks shim, at the reference's ROI markers
+        got = so.parse_ref_output(cp.stderr)
+        ref = so.parse_ref_output("\n".join(gold["lines"]))
+        assert len(got) == len(ref) == a["ns"]
+        for g, r in zip(got, ref):
+            assert abs(float(g[1]) - float(r[1])) <= 1e-9 * max(1.0, abs(float(r[1])))
+            if "nan" not in r[2] and "nan" not in g[2]:
+                assert abs(float(g[2]) - float(r[2])) <= 1e-9
