@@ -7,8 +7,9 @@ The reference tree holds no golden vectors for swaptions, so the fixtures are ou
 
   sw_<case>.json = {"args": {ns, sm, sd}, "stdout_header": "...", "lines": [the "Swaption i: [...]" stderr lines]}
 
-Every case is run through the serial build and through the FastFlow build with 1, 3 and 8 workers; all four outputs
-must be identical (asserted here), so a golden is the answer of every reference variant that can be built.
+Every case is run through the serial build, the FastFlow build with 1, 3 and 8 workers and the SkePU-OpenMP build
+(HJM_Securities_skepu_omp.cpp, sw_ref_skepu); all outputs must be identical (asserted here), so a golden is the answer
+of every reference variant that can be built.
 
 Cases:
   simsmall16      -ns 16 -sm 10000   (PARSEC simsmall; trials a multiple of BLOCK_SIZE)
@@ -42,7 +43,7 @@ CASES = {
 def main():
     for name, a in CASES.items():
         outs = []
-        for binary, nt in (("sw_ref_serial", 1), ("sw_ref_ff", 1), ("sw_ref_ff", 3), ("sw_ref_ff", 8)):
+        for binary, nt in (("sw_ref_serial", 1), ("sw_ref_ff", 1), ("sw_ref_ff", 3), ("sw_ref_ff", 8), ("sw_ref_skepu", 2)):
             if nt > a["ns"]:
                 continue
             stdout, stderr, _ = so.run_ref(a["ns"], a["sm"], nt, a["sd"], binary)
