@@ -277,13 +277,7 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
 
     const int iN = c->iN, nF = c->iFactors;
     const long long draws = (long long)(iN - 1) * nF;
-    long long sims = 0;
-    for (int i = 0; i < nSwaptions; ++i) {
-        if (!prepare(c->h_params[i], swaptions[i], iN, nF, pdYield + (size_t)i * iN, ppdFactors + (size_t)i * nF * (iN - 1),
-                     swaption_seed + i, lTrials, BLOCKSIZE))
-            return fail(c, SW_GPU_ERR_INVALID, "swaption %d: dYears/dMaturity/dTenor/dPaymentInterval put a time index outside the %d-point HJM path", i, iN);
-        sims = c->h_params[i].sims;
-    }
+    const long long sims = lTrials <= 0 ? 0 : ((lTrials + BLOCKSIZE - 1) / BLOCKSIZE) * (long long)BLOCKSIZE;  // HSB:156
     // the fast kernels: the reference drivers' shape, counters inside the range of the 32-bit residue arithmetic
     Kind kind = K_GENERIC;
     if (!(flags & SW_GPU_FLAG_IEEE) && iN == swk::FN && nF == swk::FF && swaption_seed >= 0 &&
@@ -298,6 +292,18 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         d.first = first;
         d.count = q + (g < r ? 1 : 0);
         first += d.count;
+
+        // this shard's parameter records are prepared while the devices before it already simulate
+        for (int i = d.first; i < d.first + d.count; ++i) {
+            if (!prepare(c->h_params[i], swaptions[i], iN, nF, pdYield + (size_t)i * iN, ppdFactors + (size_t)i * nF * (iN - 1),
+                         swaption_seed + i, lTrials, BLOCKSIZE)) {
+                for (int h = 0; h < g; ++h) {  // let what was launched finish before reporting
+                    if (cudaSetDevice(c->devs[h].device) == cudaSuccess) cudaStreamSynchronize(c->devs[h].stream);
+                }
+                memset(&c->timing, 0, sizeof(c->timing));
+                return fail(c, SW_GPU_ERR_INVALID, "swaption %d: dYears/dMaturity/dTenor/dPaymentInterval put a time index outside the %d-point HJM path", i, iN);
+            }
+        }
 
         const int occ = kind == K_FAST ? d.occ_fast : kind == K_LEAN ? d.occ_lean : d.occ_generic;
         const int per_sm = c->cfg_ctas_per_sm > 0 ? std::min(c->cfg_ctas_per_sm, occ) : occ;

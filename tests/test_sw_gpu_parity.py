@@ -132,7 +132,7 @@ def test_other_path_shapes_use_the_generic_kernel(iN, iFactors):
 
 def test_block_size_and_ragged_trials():
     seed, p, y, f = sw.make_portfolio(6)
-    for trials, bs in ((1, 16), (15, 16), (17, 16), (100, 7), (100, 1), (4097, 64)):
+    for trials, bs in ((0, 16), (1, 16), (15, 16), (17, 16), (100, 7), (100, 1), (4097, 64)):  # 0 trials: 0/0 = NaN, like the reference
         mean, err, tm, _ = gpu_price(p, y, f, seed, trials, 0, block_size=bs)
         omean, oerr = so.price_map(p, y, f, seed, trials, block_size=bs)
         assert tm["trials_simulated"] == 6 * ((trials + bs - 1) // bs) * bs
@@ -170,6 +170,13 @@ def test_empty_and_invalid_inputs():
         with pytest.raises(sw.SwGpuError) as ei:
             ctx.price(bad, y, f, seed, 128)
         assert ei.value.status == -1 and "swaption 1" in str(ei.value)
+        if sw.device_count() >= 2:            # an invalid swaption in the second device's shard: the first one has already started
+            with sw.SwaptionsGPU(2, num_gpus=2) as two:
+                with pytest.raises(sw.SwGpuError):
+                    two.price(bad, y, f, seed, 128)
+                m2, e2 = two.price(p, y, f, seed, 128)
+                m1, e1 = ctx.price(p, y, f, seed, 128)
+                assert m2.tobytes() == m1.tobytes()
         with pytest.raises(sw.SwGpuError):
             ctx.price(p, y, f, seed, 128, block_size=0)
         with pytest.raises(sw.SwGpuError):
