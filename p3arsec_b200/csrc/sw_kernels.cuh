@@ -393,13 +393,18 @@ __device__ __forceinline__ double path_and_payoff(const FastShared &sh, int tid,
             const double z0 = sh.z[FF * (j - 1) + 0][tid];
             const double z1 = sh.z[FF * (j - 1) + 1][tid];
             const double z2 = sh.z[FF * (j - 1) + 2][tid];
+            // lean: of row j only the entries that can still reach column 0 by step `start` or the swap leg's rates
+            // are needed: l <= (start - j) + swap_end - 1
+            const int need = LEAN ? start - j + swap_end - 1 : FN;
 #pragma unroll
             for (int l = 0; l <= FN - 1 - j; ++l) {
-                const double4 c = sh.fd[l];
-                double shock = fma(c.x, z0, c.w);
-                shock = fma(c.y, z1, shock);
-                shock = fma(c.z, z2, shock);
-                row[l] = row[l + 1] + shock;
+                if (!LEAN || l <= need) {
+                    const double4 c = sh.fd[l];
+                    double shock = fma(c.x, z0, c.w);
+                    shock = fma(c.y, z1, shock);
+                    shock = fma(c.z, z2, shock);
+                    row[l] = row[l + 1] + shock;
+                }
             }
             row[FN - j] = 0.0;  // the reference's path matrix is zero beyond the triangle
             if (j == start) {

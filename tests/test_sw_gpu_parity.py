@@ -287,3 +287,22 @@ def test_reference_driver_with_cuda_map():
             assert abs(float(g[1]) - float(r[1])) <= 1e-9 * max(1.0, abs(float(r[1])))
             if "nan" not in r[2] and "nan" not in g[2]:
                 assert abs(float(g[2]) - float(r[2])) <= 1e-9
+
+
+@pytest.mark.parametrize("mode,flags", MODES[:3])
+def test_every_swap_start_index(mode, flags):
+    """The fast kernel is specialised on iSwapStartTimeIndex = 1, 2, 3 and has a runtime-index version for the rest:
+    one swaption per start index 0..10 (ddelt = 1 year, maturity = start years, tenor up to 3 years)."""
+    n = 11
+    p = np.zeros(n, dtype=sw.SWAPTION_DTYPE)
+    p["dYears"] = 11.0
+    p["dStrike"] = 0.09
+    p["dMaturity"] = np.arange(n, dtype=np.float64)
+    p["dTenor"] = np.minimum(3.0, 10.0 - np.arange(n))
+    p["dPaymentInterval"] = 1.0
+    y = np.tile(0.05 + 0.004 * np.arange(11), (n, 1))
+    f = np.tile(sw.FACTOR_TABLE[None] * 1.5, (n, 1, 1))
+    omean, oerr = so.price_map(p, y, f, 4242, 3000)
+    assert (omean[:10] > 0).all() and omean[10] == 0.0   # start 10: nothing left of the path to pay on
+    mean, err, _, _ = gpu_price(p, y, f, 4242, 3000, flags)
+    assert_parity(mean, err, omean, oerr, 3000, "start index/" + mode)
