@@ -215,10 +215,11 @@ static int init_impl(sw_gpu_ctx *c, const int *devices, int num_gpus)
         SW_CUDA(c, cudaEventCreate(&d.ev1));
         SW_CUDA(c, cudaMalloc(&d.d_params, n * sizeof(swk::SwParams)));
         SW_CUDA(c, cudaMalloc(&d.d_out, 2 * n * sizeof(double)));
-        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
-        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(swk::FastShared)));
-        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fast, swk::sw_sim_fast<false>, swk::THREADS, sizeof(swk::FastShared)));
-        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean, swk::sw_sim_fast<true>, swk::THREADS, sizeof(swk::FastShared)));
+        const size_t full_smem = swk::fast_shared_bytes(swk::FD);
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full_smem));
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full_smem));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_fast, swk::sw_sim_fast<false>, swk::THREADS, full_smem));
+        SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean, swk::sw_sim_fast<true>, swk::THREADS, full_smem));
         SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_generic, swk::sw_sim_generic, swk::THREADS, 0));
         if (d.occ_fast < 1 || d.occ_lean < 1 || d.occ_generic < 1) return fail(c, SW_GPU_ERR_CUDA, "a kernel does not fit on device %d", d.device);
     }
@@ -305,6 +306,16 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
             }
         }
 
+        // shared memory of the fast kernels: the lean one keeps only the draws of the time steps it simulates
+        size_t smem = 0;
+        if (kind == K_FAST) smem = swk::fast_shared_bytes(swk::FD);
+        if (kind == K_LEAN) {
+            int max_start = 1;
+            for (int i = d.first; i < d.first + d.count; ++i) max_start = std::max(max_start, c->h_params[i].start);
+            smem = swk::fast_shared_bytes(swk::FF * max_start);
+            SW_CUDA(c, cudaSetDevice(d.device));
+            SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean, swk::sw_sim_fast<true>, swk::THREADS, smem));
+        }
         const int occ = kind == K_FAST ? d.occ_fast : kind == K_LEAN ? d.occ_lean : d.occ_generic;
         const int per_sm = c->cfg_ctas_per_sm > 0 ? std::min(c->cfg_ctas_per_sm, occ) : occ;
         const long long grid_threads = (long long)d.sm_count * per_sm * swk::THREADS;
@@ -336,9 +347,9 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         SW_CUDA(c, cudaMemcpyAsync(d.d_params, c->h_params + d.first, (size_t)d.count * sizeof(swk::SwParams), cudaMemcpyHostToDevice, d.stream));
         SW_CUDA(c, cudaEventRecord(d.ev0, d.stream));
         if (kind == K_FAST)
-            swk::sw_sim_fast<false><<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
+            swk::sw_sim_fast<false><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials);
         else if (kind == K_LEAN)
-            swk::sw_sim_fast<true><<<blocks, swk::THREADS, sizeof(swk::FastShared), d.stream>>>(d.d_params, geo, d.d_partials);
+            swk::sw_sim_fast<true><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials);
         else
             swk::sw_sim_generic<<<blocks, swk::THREADS, 0, d.stream>>>(d.d_params, geo, d.d_partials);
         SW_CUDA(c, cudaGetLastError());

@@ -264,12 +264,15 @@ constexpr int FN = 11, FF = 3, FD = (FN - 1) * FF;
 struct FastShared {
     double tail[swt::TAIL_DOUBLES];  // composite table of Moro's tail branch (5 KB; rows of 80 B, 16-byte aligned)
     double tab[bsm::TAB_DOUBLES];
-    double z[FD][THREADS];     // the trial's normals, [draw][thread]: conflict-free, 240 B per thread
     double4 fd[FN - 1];        // per maturity l: {fac0, fac1, fac2} * sqrt_ddelt and pdTotalDrift[l] * ddelt (two LDS.128)
     double fwd[FN];
     double pay[FN];
     double red[2][THREADS / 32];
 };
+// Behind FastShared in dynamic shared memory: z[z_rows][THREADS], the trial's normals [draw][thread] (conflict-free) --
+// all 30 draws for the full kernel, 3 x (largest swap start index of the launch) for the lean one.
+static_assert(sizeof(FastShared) % 16 == 0, "z starts 16-byte aligned");
+__host__ __device__ constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(FastShared) + (size_t)z_rows * THREADS * sizeof(double); }
 
 // ---- phase A + tail pass -----------------------------------------------------------------------------------------------
 // The trial's normals into sh.z[draw][tid].  Central branch of CumNormalInv for every draw, G draws at a time written stage
@@ -291,7 +294,7 @@ struct FastShared {
 constexpr int TAIL_TRIP = SW_TAIL_TRIP;
 
 template <bool LEAN>
-__device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, int steps)
+__device__ __forceinline__ void normals(FastShared &sh, double *__restrict__ z, int tid, uint32_t x0, int steps)
 {
     constexpr int G = LEAN ? FF : SW_PHASE_A_GROUP;
     uint32_t tail = 0;
@@ -340,15 +343,15 @@ __device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, in
         }
 #pragma unroll
         for (int i = 0; i < G; ++i) {
-            sh.z[k0 + i][tid] = fma(q[i], e[i], q[i]);  // garbage for tail draws: overwritten below
+            z[(k0 + i) * THREADS + tid] = fma(q[i], e[i], q[i]);  // garbage for tail draws: overwritten below
             if ((sg[i] - S_LO) > (S_HI - S_LO)) tail |= 1u << (k0 + i);
         }
     }
     while (tail) {
         const int k0 = __ffs(tail) - 1;
         tail &= tail - 1;
-        if (LEAN) {  // three or six draws per trial: rarely more than one tail draw per lane
-            sh.z[k0][tid] = tail_normal(x0, k0, sh.tab, sh.tail);
+        if (LEAN) {  // three or six draws per trial: rarely more than one tail draw per lane (two per trip measured 8 % slower)
+            z[k0 * THREADS + tid] = tail_normal(x0, k0, sh.tab, sh.tail);
         } else {
             // TRIP draws per trip with interleaved chains; with fewer left the last trip repeats draw k0
             int kk[TAIL_TRIP];
@@ -362,7 +365,7 @@ __device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, in
 #pragma unroll
             for (int i = 0; i < TAIL_TRIP; ++i) zz[i] = tail_normal(x0, kk[i], sh.tab, sh.tail);
 #pragma unroll
-            for (int i = 0; i < TAIL_TRIP; ++i) sh.z[kk[i]][tid] = zz[i];
+            for (int i = 0; i < TAIL_TRIP; ++i) z[kk[i] * THREADS + tid] = zz[i];
         }
     }
 }
@@ -374,7 +377,7 @@ __device__ __forceinline__ void normals(FastShared &sh, int tid, uint32_t x0, in
 // whole phase is one basic block; START < 0: taken from start_rt.  Every exponential is evaluated branch-free; `worst`
 // remembers whether one of them left the fast range.
 template <bool LEAN, int START>
-__device__ __forceinline__ double path_and_payoff(const FastShared &sh, int tid, double ddelt, double swap_ddelt, int start_rt,
+__device__ __forceinline__ double path_and_payoff(const FastShared &sh, const double *__restrict__ z, int tid, double ddelt, double swap_ddelt, int start_rt,
                                                   int swap_end, uint32_t &worst)
 {
     const int start = START >= 0 ? START : start_rt;
@@ -390,9 +393,9 @@ __device__ __forceinline__ double path_and_payoff(const FastShared &sh, int tid,
     for (int j = 1; j <= FN - 1; ++j) {
         if (!LEAN || j <= steps) {
             run *= exp_tracked(-row[0] * ddelt, sh.tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
-            const double z0 = sh.z[FF * (j - 1) + 0][tid];
-            const double z1 = sh.z[FF * (j - 1) + 1][tid];
-            const double z2 = sh.z[FF * (j - 1) + 2][tid];
+            const double z0 = z[(FF * (j - 1) + 0) * THREADS + tid];
+            const double z1 = z[(FF * (j - 1) + 1) * THREADS + tid];
+            const double z2 = z[(FF * (j - 1) + 2) * THREADS + tid];
             // lean: of row j only the entries that can still reach column 0 by step `start` or the swap leg's rates
             // are needed: l <= (start - j) + swap_end - 1
             const int need = LEAN ? start - j + swap_end - 1 : FN;
@@ -431,12 +434,16 @@ __device__ __forceinline__ double path_and_payoff(const FastShared &sh, int tid,
 
 // Four CTAs (16 warps) per SM: 128 registers per thread.  Builds bounded for 5 and 6 CTAs (96 / 80 registers) spill
 // the path rows and measured 4-12 % slower.
+#ifndef SW_LEAN_MINB
+#define SW_LEAN_MINB 5  /* lean kernel: 5 CTAs per SM (96 registers) measured best: 46.6 / 48.7 / 45.9 G trials/s for 4 / 5 / 8 */
+#endif
 template <bool LEAN>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, LEAN ? SW_LEAN_MINB : 4)
 sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
+    double *const z = reinterpret_cast<double *>(smem_raw + sizeof(FastShared));
     const int tid = threadIdx.x;
     bsm::fill_tables(sh.tab, tid, THREADS);
     swt::fill_tail(sh.tail, tid, THREADS);
@@ -480,17 +487,17 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             if (t >= sims) break;
 
             // ---- phase A + tail pass: the trial's normals into sh.z (see normals())
-            normals<LEAN>(sh, tid, ru_residue(seed + t * FD), steps);
+            normals<LEAN>(sh, z, tid, ru_residue(seed + t * FD), steps);
 
             // ---- phase B: path, discount factors, payoff; specialised on the swap start index (1..3 covers every
             // swaption the reference drivers create: dMaturity = 1, dYears in [5, 20))
             uint32_t worst = 0;
             double disc;
             switch (start) {
-                case 1: disc = path_and_payoff<LEAN, 1>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                case 2: disc = path_and_payoff<LEAN, 2>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                case 3: disc = path_and_payoff<LEAN, 3>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                default: disc = path_and_payoff<LEAN, -1>(sh, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 1: disc = path_and_payoff<LEAN, 1>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 2: disc = path_and_payoff<LEAN, 2>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 3: disc = path_and_payoff<LEAN, 3>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                default: disc = path_and_payoff<LEAN, -1>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
             }
             if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[sw], FN, FF, t);
             sum += disc;                                                  // HSB:203
