@@ -73,6 +73,11 @@ typedef struct sw_gpu_swaption {
                                 whenever all intermediate values are finite.  Off by default: the default kernel
                                 does the reference's full amount of work per trial                                 */
 
+#define SW_GPU_FLAG_BATCHED 4u /* always simulate all swaptions in one kernel launch (tables in shared memory).  By default the
+                                full-work kernel gives a swaption with >= 262144 trials a launch of its own, with its factor /
+                                drift / yield tables in the kernel-parameter constant bank, which is 10 % faster (DESIGN.md
+                                9.3); results are identical either way up to the order of the final summation        */
+
 typedef struct sw_gpu_timing {
     double roi_ms;       /* last sw_gpu_price: device time of the kernels, max over devices (CUDA events)          */
     double wall_ms;      /* host wall clock of the last sw_gpu_price call, copies included                         */

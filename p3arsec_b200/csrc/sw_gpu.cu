@@ -33,11 +33,18 @@
 
 namespace {
 
+enum { AUX_STREAMS = 3 };
+// A swaption gets a kernel launch of its own (tables in the constant bank: sw_sim_one) from this many simulated trials
+// on; below it one kernel walks over all (swaption, chunk) items with the tables in shared memory (sw_sim_fast).
+const long long ONE_SWAPTION_MIN_TRIALS = 262144;
+
 struct Dev {
     int device = 0;
     int sm_count = 0;
     int first = 0, count = 0;  // shard of the last call
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[AUX_STREAMS] = {nullptr};     // one-swaption launches rotate over stream + aux so that their tails overlap
+    cudaEvent_t aux_done[AUX_STREAMS] = {nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     swk::SwParams *d_params = nullptr;
     double2 *d_partials = nullptr;
@@ -187,6 +194,10 @@ void sw_gpu_fini(sw_gpu_ctx *ctx)
         if (d.d_out) cudaFree(d.d_out);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
+        for (int k = 0; k < AUX_STREAMS; ++k) {
+            if (d.aux_done[k]) cudaEventDestroy(d.aux_done[k]);
+            if (d.aux[k]) cudaStreamDestroy(d.aux[k]);
+        }
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
@@ -211,6 +222,12 @@ static int init_impl(sw_gpu_ctx *c, const int *devices, int num_gpus)
         if (prop.major < 10) return fail(c, SW_GPU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", d.device, prop.major, prop.minor);
         d.sm_count = prop.multiProcessorCount;
         SW_CUDA(c, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        for (int k = 0; k < AUX_STREAMS; ++k) {
+            SW_CUDA(c, cudaStreamCreateWithFlags(&d.aux[k], cudaStreamNonBlocking));
+            SW_CUDA(c, cudaEventCreateWithFlags(&d.aux_done[k], cudaEventDisableTiming));
+        }
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_one<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swk::one_shared_bytes(swk::FD)));
+        SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_one<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swk::one_shared_bytes(swk::FD)));
         SW_CUDA(c, cudaEventCreate(&d.ev0));
         SW_CUDA(c, cudaEventCreate(&d.ev1));
         SW_CUDA(c, cudaMalloc(&d.d_params, n * sizeof(swk::SwParams)));
@@ -270,7 +287,7 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
     if (nSwaptions < 0 || nSwaptions > c->max_swaptions || (nSwaptions > 0 && (!swaptions || !pdYield || !ppdFactors || !mean || !std_error)))
         return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: bad arguments (nSwaptions = %d, capacity %d)", nSwaptions, c->max_swaptions);
     if (BLOCKSIZE < 1 || lTrials < 0) return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: BLOCKSIZE %d, lTrials %ld", BLOCKSIZE, lTrials);
-    if (flags & ~(SW_GPU_FLAG_IEEE | SW_GPU_FLAG_LEAN)) return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: unknown flags 0x%x", flags);
+    if (flags & ~(SW_GPU_FLAG_IEEE | SW_GPU_FLAG_LEAN | SW_GPU_FLAG_BATCHED)) return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: unknown flags 0x%x", flags);
     const auto w0 = std::chrono::steady_clock::now();
     memset(&c->timing, 0, sizeof(c->timing));
     c->shards_used = 0;
@@ -307,23 +324,34 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         }
 
         // shared memory of the fast kernels: the lean one keeps only the draws of the time steps it simulates
-        size_t smem = 0;
-        if (kind == K_FAST) smem = swk::fast_shared_bytes(swk::FD);
+        // (full kernel only: a lean launch of one swaption is too short -- 20 us per million trials -- and measured 33 % slower)
+        const bool one = kind == K_FAST && !(flags & SW_GPU_FLAG_BATCHED) && sims >= ONE_SWAPTION_MIN_TRIALS;
+        int z_rows = swk::FD;
         if (kind == K_LEAN) {
             int max_start = 1;
             for (int i = d.first; i < d.first + d.count; ++i) max_start = std::max(max_start, c->h_params[i].start);
-            smem = swk::fast_shared_bytes(swk::FF * max_start);
-            SW_CUDA(c, cudaSetDevice(d.device));
-            SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ_lean, swk::sw_sim_fast<true>, swk::THREADS, smem));
+            z_rows = swk::FF * max_start;
         }
-        const int occ = kind == K_FAST ? d.occ_fast : kind == K_LEAN ? d.occ_lean : d.occ_generic;
+        const size_t smem = kind == K_GENERIC ? 0 : one ? swk::one_shared_bytes(z_rows) : swk::fast_shared_bytes(z_rows);
+        SW_CUDA(c, cudaSetDevice(d.device));
+        int occ = d.occ_generic;
+        if (kind == K_FAST) {
+            if (one) SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, swk::sw_sim_one<false>, swk::THREADS, smem));
+            else occ = d.occ_fast;
+        } else if (kind == K_LEAN) {
+            if (one) SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, swk::sw_sim_one<true>, swk::THREADS, smem));
+            else SW_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, swk::sw_sim_fast<true>, swk::THREADS, smem));
+        }
+        if (occ < 1) return fail(c, SW_GPU_ERR_CUDA, "kernel does not fit on device %d", d.device);
         const int per_sm = c->cfg_ctas_per_sm > 0 ? std::min(c->cfg_ctas_per_sm, occ) : occ;
-        const long long grid_threads = (long long)d.sm_count * per_sm * swk::THREADS;
-        // trials per thread per item: enough items for ~8 per resident CTA (static round-robin balance), capped
+        const long long grid_ctas = (long long)d.sm_count * per_sm;
+        const long long grid_threads = grid_ctas * swk::THREADS;
+        // trials per thread per item.  Batched kernel: enough items for ~8 per resident CTA (static round-robin balance),
+        // capped.  One swaption per launch: one item per CTA, the swaption's trials spread over the whole grid.
         int tpt = c->cfg_tpt;
         if (tpt <= 0) {
-            const long long want = (sims * d.count) / (grid_threads * 8);
-            tpt = (int)std::max<long long>(1, std::min<long long>(64, want));
+            const long long want = one ? (sims + grid_threads - 1) / grid_threads : (sims * d.count) / (grid_threads * 8);
+            tpt = (int)std::max<long long>(1, std::min<long long>(one ? 4096 : 64, want));
         }
         swk::Geom geo;
         geo.iN = iN;
@@ -334,9 +362,8 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         if (chunks * d.count > 0x7fffffffLL) return fail(c, SW_GPU_ERR_INVALID, "too many work items");
         geo.chunks = (int)chunks;
         geo.items = (int)(chunks * d.count);
-        const int blocks = (int)std::min<long long>(geo.items, (long long)d.sm_count * per_sm);
+        const int blocks = (int)std::min<long long>(one ? chunks : (long long)geo.items, grid_ctas);
 
-        SW_CUDA(c, cudaSetDevice(d.device));
         if ((size_t)geo.items > d.partial_cap) {
             if (d.d_partials) SW_CUDA(c, cudaFree(d.d_partials));
             d.d_partials = nullptr;
@@ -346,7 +373,41 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         }
         SW_CUDA(c, cudaMemcpyAsync(d.d_params, c->h_params + d.first, (size_t)d.count * sizeof(swk::SwParams), cudaMemcpyHostToDevice, d.stream));
         SW_CUDA(c, cudaEventRecord(d.ev0, d.stream));
-        if (kind == K_FAST)
+        if (one) {
+            for (int k = 0; k < AUX_STREAMS; ++k) SW_CUDA(c, cudaStreamWaitEvent(d.aux[k], d.ev0, 0));
+            for (int i = 0; i < d.count; ++i) {
+                const swk::SwParams &H = c->h_params[d.first + i];
+                swk::OneSwaption P;
+                memset(&P, 0, sizeof(P));
+                for (int l = 0; l < swk::FN - 1; ++l)
+                    P.fd[l] = make_double4(H.fac[0][l] * H.sqrt_ddelt, H.fac[1][l] * H.sqrt_ddelt, H.fac[2][l] * H.sqrt_ddelt, H.driftdt[l]);
+                for (int l = 0; l < swk::FN; ++l) {
+                    P.fwd[l] = H.fwd[l];
+                    P.pay[l] = H.pay[l];
+                }
+                P.ddelt = H.ddelt;
+                P.swap_ddelt = H.swap_ddelt;
+                P.seed = H.seed;
+                P.sims = H.sims;
+                P.chunk_trials = geo.chunk_trials;
+                P.start = H.start;
+                P.len = H.len;
+                P.last_pay = H.last_pay;
+                P.tpt = tpt;
+                P.chunks = geo.chunks;
+                P.partial_base = i * geo.chunks;
+                P.sw_index = i;
+                cudaStream_t st = (i % (AUX_STREAMS + 1)) == 0 ? d.stream : d.aux[(i % (AUX_STREAMS + 1)) - 1];
+                if (kind == K_FAST) swk::sw_sim_one<false><<<blocks, swk::THREADS, smem, st>>>(P, d.d_params, d.d_partials);
+                else swk::sw_sim_one<true><<<blocks, swk::THREADS, smem, st>>>(P, d.d_params, d.d_partials);
+            }
+            SW_CUDA(c, cudaGetLastError());
+            for (int k = 0; k < AUX_STREAMS; ++k) {
+                SW_CUDA(c, cudaEventRecord(d.aux_done[k], d.aux[k]));
+                SW_CUDA(c, cudaStreamWaitEvent(d.stream, d.aux_done[k], 0));
+            }
+            c->timing.kernel_launches += (unsigned long long)d.count - 1;
+        } else if (kind == K_FAST)
             swk::sw_sim_fast<false><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials);
         else if (kind == K_LEAN)
             swk::sw_sim_fast<true><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials);

@@ -294,7 +294,8 @@ __host__ __device__ constexpr size_t fast_shared_bytes(int z_rows) { return size
 constexpr int TAIL_TRIP = SW_TAIL_TRIP;
 
 template <bool LEAN>
-__device__ __forceinline__ void normals(FastShared &sh, double *__restrict__ z, int tid, uint32_t x0, int steps)
+__device__ __forceinline__ void normals(const double *__restrict__ tab, const double *__restrict__ tailtab, double *__restrict__ z, int tid, uint32_t x0,
+                                        int steps)
 {
     constexpr int G = LEAN ? FF : SW_PHASE_A_GROUP;
     uint32_t tail = 0;
@@ -351,7 +352,7 @@ __device__ __forceinline__ void normals(FastShared &sh, double *__restrict__ z, 
         const int k0 = __ffs(tail) - 1;
         tail &= tail - 1;
         if (LEAN) {  // three or six draws per trial: rarely more than one tail draw per lane (two per trip measured 8 % slower)
-            z[k0 * THREADS + tid] = tail_normal(x0, k0, sh.tab, sh.tail);
+            z[k0 * THREADS + tid] = tail_normal(x0, k0, tab, tailtab);
         } else {
             // TRIP draws per trip with interleaved chains; with fewer left the last trip repeats draw k0
             int kk[TAIL_TRIP];
@@ -363,7 +364,7 @@ __device__ __forceinline__ void normals(FastShared &sh, double *__restrict__ z, 
                 tail &= tail - 1;  // (0 & anything == 0)
             }
 #pragma unroll
-            for (int i = 0; i < TAIL_TRIP; ++i) zz[i] = tail_normal(x0, kk[i], sh.tab, sh.tail);
+            for (int i = 0; i < TAIL_TRIP; ++i) zz[i] = tail_normal(x0, kk[i], tab, tailtab);
 #pragma unroll
             for (int i = 0; i < TAIL_TRIP; ++i) z[kk[i] * THREADS + tid] = zz[i];
         }
@@ -376,9 +377,11 @@ __device__ __forceinline__ void normals(FastShared &sh, double *__restrict__ z, 
 // START >= 0: the swap start index as a compile-time constant -- the row snapshot is then a register renaming and the
 // whole phase is one basic block; START < 0: taken from start_rt.  Every exponential is evaluated branch-free; `worst`
 // remembers whether one of them left the fast range.
-template <bool LEAN, int START>
-__device__ __forceinline__ double path_and_payoff(const FastShared &sh, const double *__restrict__ z, int tid, double ddelt, double swap_ddelt, int start_rt,
-                                                  int swap_end, uint32_t &worst)
+// SRC = where the swaption's tables (fd, fwd, pay) are read from: FastShared (shared memory, any swaption per work item)
+// or OneSwaption (kernel-parameter constant bank, one swaption per launch).
+template <bool LEAN, int START, class SRC>
+__device__ __forceinline__ double path_and_payoff(const SRC &sh, const double *__restrict__ tab, const double *__restrict__ z, int tid, double ddelt,
+                                                  double swap_ddelt, int start_rt, int swap_end, uint32_t &worst)
 {
     const int start = START >= 0 ? START : start_rt;
     const int steps = LEAN ? start : FN - 1;  // time steps whose shocks are needed
@@ -392,7 +395,7 @@ __device__ __forceinline__ double path_and_payoff(const FastShared &sh, const do
 #pragma unroll
     for (int j = 1; j <= FN - 1; ++j) {
         if (!LEAN || j <= steps) {
-            run *= exp_tracked(-row[0] * ddelt, sh.tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
+            run *= exp_tracked(-row[0] * ddelt, tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
             const double z0 = z[(FF * (j - 1) + 0) * THREADS + tid];
             const double z1 = z[(FF * (j - 1) + 1) * THREADS + tid];
             const double z2 = z[(FF * (j - 1) + 2) * THREADS + tid];
@@ -424,7 +427,7 @@ __device__ __forceinline__ double path_and_payoff(const FastShared &sh, const do
 #pragma unroll
     for (int i = 1; i <= FN - 1; ++i) {
         if (!LEAN || i <= swap_end) {
-            df *= exp_tracked(-srow[i - 1] * swap_ddelt, sh.tab, worst);
+            df *= exp_tracked(-srow[i - 1] * swap_ddelt, tab, worst);
             fixed = fma(sh.pay[i], df, fixed);
         }
     }
@@ -487,17 +490,17 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             if (t >= sims) break;
 
             // ---- phase A + tail pass: the trial's normals into sh.z (see normals())
-            normals<LEAN>(sh, z, tid, ru_residue(seed + t * FD), steps);
+            normals<LEAN>(sh.tab, sh.tail, z, tid, ru_residue(seed + t * FD), steps);
 
             // ---- phase B: path, discount factors, payoff; specialised on the swap start index (1..3 covers every
             // swaption the reference drivers create: dMaturity = 1, dYears in [5, 20))
             uint32_t worst = 0;
             double disc;
             switch (start) {
-                case 1: disc = path_and_payoff<LEAN, 1>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                case 2: disc = path_and_payoff<LEAN, 2>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                case 3: disc = path_and_payoff<LEAN, 3>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                default: disc = path_and_payoff<LEAN, -1>(sh, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 1: disc = path_and_payoff<LEAN, 1>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 2: disc = path_and_payoff<LEAN, 2>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 3: disc = path_and_payoff<LEAN, 3>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                default: disc = path_and_payoff<LEAN, -1>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
             }
             if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[sw], FN, FF, t);
             sum += disc;                                                  // HSB:203
@@ -506,6 +509,68 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
 
         block_sum2(sum, sumsq, sh.red);
         if (tid == 0) partials[item] = make_double2(sum, sumsq);
+    }
+}
+
+// =====================================================================================================================
+// sw_sim_one: the same trial code for ONE swaption per launch, its tables in the kernel-parameter constant bank.
+// A DFMA whose three operands are three different register pairs issues every 3.07 scheduler cycles on B200, one with a
+// constant-bank operand every 2.07 (profiles/r01_dfma_operands_microbench.txt).  In sw_sim_fast the factor table comes from
+// shared memory, so the 165 shock FMAs of a trial are of the slow kind and need 110 LDS.128 on top; here fd[l], fwd[l]
+// and pay[i] are immediates of the instruction (c[0x0][imm]).  Used when a swaption has enough trials to fill the GPU.
+// =====================================================================================================================
+struct OneSwaption {
+    double4 fd[FN - 1];  // {fac0, fac1, fac2} * sqrt_ddelt and pdTotalDrift * ddelt per maturity
+    double fwd[FN];
+    double pay[FN];
+    double ddelt, swap_ddelt;
+    long long seed, sims, chunk_trials;
+    int start, len, last_pay, tpt;
+    int chunks, partial_base, sw_index, pad;
+};
+
+struct OneShared {
+    double tail[swt::TAIL_DOUBLES];
+    double tab[bsm::TAB_DOUBLES];
+    double red[2][THREADS / 32];
+};
+static_assert(sizeof(OneShared) % 16 == 0, "z starts 16-byte aligned");
+__host__ __device__ constexpr size_t one_shared_bytes(int z_rows) { return sizeof(OneShared) + (size_t)z_rows * THREADS * sizeof(double); }
+
+template <bool LEAN>
+__global__ void __launch_bounds__(THREADS, LEAN ? SW_LEAN_MINB : 4)
+sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ params, double2 *__restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OneShared &sh = *reinterpret_cast<OneShared *>(smem_raw);
+    double *const z = reinterpret_cast<double *>(smem_raw + sizeof(OneShared));
+    const int tid = threadIdx.x;
+    bsm::fill_tables(sh.tab, tid, THREADS);
+    swt::fill_tail(sh.tail, tid, THREADS);
+    const int steps = LEAN ? P.start : FN - 1;
+    const int swap_end = LEAN ? P.last_pay : P.len - 1;
+
+    for (int chunk = blockIdx.x; chunk < P.chunks; chunk += gridDim.x) {
+        __syncthreads();  // tables filled / previous chunk's reduction read
+        double sum = 0.0, sumsq = 0.0;
+        for (int m = 0; m < P.tpt; ++m) {
+            const long long t = (long long)chunk * P.chunk_trials + (long long)m * THREADS + tid;
+            if (t >= P.sims) break;
+            normals<LEAN>(sh.tab, sh.tail, z, tid, ru_residue(P.seed + t * FD), steps);
+            uint32_t worst = 0;
+            double disc;
+            switch (P.start) {
+                case 1: disc = path_and_payoff<LEAN, 1>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                case 2: disc = path_and_payoff<LEAN, 2>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                case 3: disc = path_and_payoff<LEAN, 3>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                default: disc = path_and_payoff<LEAN, -1>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+            }
+            if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[P.sw_index], FN, FF, t);
+            sum += disc;                     // HSB:203
+            sumsq = fma(disc, disc, sumsq);  // HSB:204
+        }
+        block_sum2(sum, sumsq, sh.red);
+        if (tid == 0) partials[P.partial_base + chunk] = make_double2(sum, sumsq);
     }
 }
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsw_gpu.so")
 ABI_VERSION = 1
 
-FLAG_IEEE, FLAG_LEAN = 1, 2
+FLAG_IEEE, FLAG_LEAN, FLAG_BATCHED = 1, 2, 4
 MAX_N, MAX_FACTORS = 32, 8
 BLOCK_SIZE = 16              # PARSEC HJM_type.h, passed at HJM_Securities.cpp:319
 DEFAULT_NUM_TRIALS = 102400  # PARSEC HJM_type.h, HJM_Securities.cpp:53

@@ -77,7 +77,7 @@ def test_reference_command_lines_match_committed_reference_output(name, mode, fl
         assert np.abs(err[ok] - rerr[ok]).max() <= 1e-9
     omean, oerr = so.price_map(p, y, f, seed, a["sm"])
     assert_parity(mean, err, omean, oerr, a["sm"], "%s/%s" % (name, mode))
-    assert tm["kernel_launches"] == 2 and tm["trials_simulated"] == a["ns"] * ((a["sm"] + 15) // 16) * 16
+    assert tm["kernel_launches"] == 2 and tm["trials_simulated"] == a["ns"] * ((a["sm"] + 15) // 16) * 16   # few trials: one batched launch + finalize
 
 
 @pytest.mark.parametrize("mode,flags", MODES)
@@ -306,3 +306,23 @@ def test_every_swap_start_index(mode, flags):
     assert (omean[:10] > 0).all() and omean[10] == 0.0   # start 10: nothing left of the path to pay on
     mean, err, _, _ = gpu_price(p, y, f, 4242, 3000, flags)
     assert_parity(mean, err, omean, oerr, 3000, "start index/" + mode)
+
+
+def test_one_swaption_per_launch_path_against_oracle_and_batched_kernel():
+    """From 262144 trials per swaption on, every swaption gets a launch of its own with its tables in the constant
+    bank (sw_sim_one); SW_GPU_FLAG_BATCHED forces the single-launch kernel.  Both against the oracle, and each other."""
+    seed, p, y, f = sw.make_portfolio(5)
+    trials = 262144 + 48
+    omean, oerr = so.price_map(p, y, f, seed, trials)
+    for mode, flags in (("fast", 0), ("lean", sw.FLAG_LEAN)):
+        one = gpu_price(p, y, f, seed, trials, flags)
+        bat = gpu_price(p, y, f, seed, trials, flags | sw.FLAG_BATCHED)
+        assert one[2]["kernel_launches"] == (5 + 1 if mode == "fast" else 2) and bat[2]["kernel_launches"] == 2  # lean always batches
+        assert_parity(one[0], one[1], omean, oerr, trials, "one/" + mode)
+        assert_parity(bat[0], bat[1], omean, oerr, trials, "batched/" + mode)
+        np.testing.assert_allclose(one[0], bat[0], rtol=1e-13)
+    # a geometry that gives a launch several chunks per CTA, and a seed that makes a trial hit the generator's modulus
+    hit = 2147483647 - 30 * 1000
+    omean, oerr = so.price_map(p[:2], y[:2], f[:2], hit, trials)
+    got = gpu_price(p[:2], y[:2], f[:2], hit, trials, 0, geometry=(2, 3))
+    assert_parity(got[0], got[1], omean, oerr, trials, "one/modulus")

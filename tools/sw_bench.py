@@ -115,7 +115,8 @@ def ours(args):
     torch.cuda.set_device(local_rank)
     ranks = Ranks(backend="nccl", device=torch.device("cuda", local_rank))
     n_gpus = world * in_process_gpus
-    flags = {"fast": 0, "lean": sw.FLAG_LEAN, "ieee": sw.FLAG_IEEE}[args.mode]
+    flags = {"fast": 0, "lean": sw.FLAG_LEAN, "ieee": sw.FLAG_IEEE}[args.mode] | (sw.FLAG_BATCHED if args.batched else 0)
+    one_per_launch = args.mode == "fast" and not args.batched and ((trials + 15) // 16) * 16 >= 262144
 
     seed, p, y, f = sw.make_portfolio(ns)
     first, count = shard_range(ns, world, rank)
@@ -190,7 +191,7 @@ def ours(args):
                 "peak_source": counts.get("fp64_peak_source") or "nominal",
                 "nominal_peak": nominal, "frac_of_nominal": (achieved / nominal) if achieved else None,
                 "nominal_source": "%d SMs x %d FP64 lanes x %d MHz (clock sampled during the run)" % (props.multi_processor_count, FP64_LANES_PER_SM, sm_mhz),
-                "kernel": "swk::sw_sim_fast<%s>" % ("true" if args.mode == "lean" else "false") if args.mode != "ieee" else "swk::sw_sim_generic",
+                "kernel": ("swk::sw_sim_one<%s>" if one_per_launch else "swk::sw_sim_fast<%s>") % ("true" if args.mode == "lean" else "false") if args.mode != "ieee" else "swk::sw_sim_generic",
                 "fp64_pipe_instructions_per_trial": ipt, "trials_per_launch": int(sims_local / args.steps / max(in_process_gpus, 1)),
                 "avg_launch_us": dev_ms / args.steps * 1e3,
                 "note": "instructions per trial come from profiles/sw_ncu_counts.json (ncu smsp__inst_executed_pipe_fp64 x 32 / trials)"}
@@ -210,6 +211,7 @@ def ours(args):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "swaptions": ns, "trials_per_swaption": trials, "mode": args.mode, "block_size": sw.BLOCK_SIZE,
+                       "launches": "one kernel per swaption (tables in the constant bank) + finalize" if one_per_launch else "one kernel for the portfolio + finalize",
                        "parallelism": "%d contiguous shards of the portfolio, no collective" % n_gpus,
                        "l2": "not applicable: a trial reads no global memory (per-swaption parameters sit in shared memory), so there is nothing to flush",
                        "step": "one ROI = the Map over the whole portfolio (HJM_Securities.cpp:311-323)"},
@@ -235,6 +237,7 @@ def main(argv=None):
     ap.add_argument("--trials", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--tpt", type=int, default=0)
+    ap.add_argument("--batched", action="store_true", help="SW_GPU_FLAG_BATCHED: one kernel launch for the whole portfolio")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args(argv)
     if args.warmup < 3 and args.impl == "ours":
