@@ -192,8 +192,10 @@ def ours(args):
                 "nominal_peak": nominal, "frac_of_nominal": (achieved / nominal) if achieved else None,
                 "nominal_source": "%d SMs x %d FP64 lanes x %d MHz (clock sampled during the run)" % (props.multi_processor_count, FP64_LANES_PER_SM, sm_mhz),
                 "kernel": ("swk::sw_sim_one<%s>" if one_per_launch else "swk::sw_sim_fast<%s>") % ("true" if args.mode == "lean" else "false") if args.mode != "ieee" else "swk::sw_sim_generic",
-                "fp64_pipe_instructions_per_trial": ipt, "trials_per_launch": int(sims_local / args.steps / max(in_process_gpus, 1)),
-                "avg_launch_us": dev_ms / args.steps * 1e3,
+                "fp64_pipe_instructions_per_trial": ipt, "trials_per_roi_per_gpu": int(sims_local / args.steps / max(in_process_gpus, 1)),
+                "roi_us": dev_ms / args.steps * 1e3, "launches_per_roi_per_gpu": launches // args.steps // max(in_process_gpus, 1),
+                "launch_note": "one sw_sim_one launch per swaption, rotating over 4 streams so that their tails overlap, + sw_finalize; the ROI is timed "
+                               "with CUDA events around all of them" if one_per_launch else "one simulation launch + sw_finalize per ROI",
                 "note": "instructions per trial come from profiles/sw_ncu_counts.json (ncu smsp__inst_executed_pipe_fp64 x 32 / trials)"}
 
     cpu = None
