@@ -321,6 +321,10 @@ def test_one_swaption_per_launch_path_against_oracle_and_batched_kernel():
         assert_parity(one[0], one[1], omean, oerr, trials, "one/" + mode)
         assert_parity(bat[0], bat[1], omean, oerr, trials, "batched/" + mode)
         np.testing.assert_allclose(one[0], bat[0], rtol=1e-13)
+        if sw.device_count() >= 2:   # the per-swaption launches of two devices run at the same time
+            two = gpu_price(p, y, f, seed, trials, flags, num_gpus=2)
+            assert two[0].tobytes() == one[0].tobytes() and two[1].tobytes() == one[1].tobytes()
+            assert two[2]["kernel_launches"] == (5 + 2 if mode == "fast" else 4)
     # a geometry that gives a launch several chunks per CTA, and a seed that makes a trial hit the generator's modulus
     hit = 2147483647 - 30 * 1000
     omean, oerr = so.price_map(p[:2], y[:2], f[:2], hit, trials)
