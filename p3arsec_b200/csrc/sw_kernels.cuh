@@ -13,10 +13,20 @@
  * partial[item] = {sum, sum of squares}; sw_finalize adds the partials of each swaption in a fixed tree and applies
  * HSB:212-214.  No atomics on the data path: the result is deterministic for a given geometry.
  *
- * This is an FP64-pipe-bound kernel (no tensor cores: nothing is a contraction; ~2 KB of parameters per swaption
- * and 16 bytes of output per item, so HBM is idle).  sw_sim_fast keeps the per-trial state in registers and its
- * 30 normals in shared memory ([draw][thread], conflict-free); the CumNormalInv tail branch (16 % of the draws,
- * two logarithms) is deferred and executed only for the draws that need it instead of diverging 30 times.
+ * These are FP64-pipe-bound kernels (no tensor cores: nothing is a contraction; ~1.2 KB of parameters per swaption
+ * and 16 bytes of output per item, so HBM is idle).  Kernels, all built from the same device functions:
+ *   sw_sim_fast<LEAN>  iN = 11, iFactors = 3; all (swaption, chunk) items of a device in ONE launch, the swaption's
+ *                      tables in shared memory.  Per-trial state in registers, the trial's normals in shared memory
+ *                      ([draw][thread], conflict-free).  LEAN = only what the price depends on.
+ *   sw_sim_one<LEAN>   the same for ONE swaption per launch, its tables in the kernel-parameter constant bank, so that
+ *                      the FP64 pipe gets them as uniform-register operands (a DFMA with three register-pair operands
+ *                      issues every 3.07 cycles on B200, one with a constant operand every 2.07); the host uses it
+ *                      for the full kernel when a swaption has enough trials to fill the GPU.
+ *   sw_sim_generic     any shape, the reference's operation order (generic_trial), also the out-of-range fallback.
+ *   sw_finalize        partial sums -> mean and standard error.
+ * Building blocks: normals() = phase A (30 central-branch CumNormalInv, staged six at a time) + the deferred tail pass
+ * (Moro's tail branch only for the draws that need it, through the composite table of sw_tail.h);
+ * path_and_payoff<LEAN, START> = phase B, specialised on the swap start index.  DESIGN.md section 9 has the numbers.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -42,7 +52,7 @@ struct SwParams {
     double ddelt;                // HSB:48
     double sqrt_ddelt;           // HJM_SimPath_Forward_Blocking
     double swap_ddelt;           // dSwapVectorYears / iSwapVectorLength (Discount_Factors_Blocking at HSB:184)
-    double inv_trials_unused;
+    double reserved;
     long long seed;              // swaption_seed + i (HJM_Securities.cpp:319)
     long long trials;            // lTrials
     long long sims;              // ceil(lTrials / BLOCKSIZE) * BLOCKSIZE (HSB:156)
