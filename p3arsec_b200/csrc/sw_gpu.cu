@@ -30,6 +30,7 @@
 
 #include "../../include/sw_gpu.h"
 #include "sw_kernels.cuh"
+#include "sw_prepare.h"
 
 namespace {
 
@@ -88,68 +89,6 @@ int fail(sw_gpu_ctx *c, int status, const char *fmt, ...)
             return fail((c), e_ == cudaErrorMemoryAllocation ? SW_GPU_ERR_NOMEM : SW_GPU_ERR_CUDA, "%s: %s", \
                         #call, cudaGetErrorString(e_));                                                       \
     } while (0)
-
-// Everything HJM_Swaption_Blocking derives before the trial loop.  Returns false where the reference would index
-// outside its vectors (it has no checks of its own).
-bool prepare(swk::SwParams &P, const sw_gpu_swaption &s, int iN, int iFactors, const double *pdYield,
-             const double *ppdFactors, long seed, long lTrials, int BLOCKSIZE)
-{
-    memset(&P, 0, sizeof(P));
-    const double ddelt = (double)(s.dYears / iN);                                  // HSB:48
-    if (!(ddelt > 0.0) || !std::isfinite(ddelt)) return false;
-    const double fr = s.dPaymentInterval / ddelt + 0.5, st = s.dMaturity / ddelt + 0.5, tp = s.dTenor / ddelt + 0.5;
-    const double vl = iN - s.dMaturity / ddelt + 0.5;
-    if (!(fabs(fr) < 1e6 && fabs(st) < 1e6 && fabs(tp) < 1e6 && fabs(vl) < 1e6)) return false;
-    const int iFreqRatio = (int)fr;                                                // HSB:50
-    double dStrikeCont;
-    if (s.dCompounding == 0) dStrikeCont = s.dStrike;                              // HSB:56-57
-    else dStrikeCont = (1 / s.dCompounding) * log(1 + s.dStrike * s.dCompounding);  // HSB:61
-    const int iSwapVectorLength = (int)vl;                                         // HSB:116
-    const int iSwapStartTimeIndex = (int)st;                                       // HSB:125
-    const int iSwapTimePoints = (int)tp;                                           // HSB:126
-    const double dSwapVectorYears = (double)(iSwapVectorLength * ddelt);           // HSB:127
-    if (iSwapVectorLength < 1 || iSwapVectorLength > iN || iSwapStartTimeIndex < 0 || iSwapStartTimeIndex > iN - 1 ||
-        iFreqRatio < 1 || iSwapTimePoints > iSwapVectorLength - 1)
-        return false;
-
-    for (int i = iFreqRatio; i <= iSwapTimePoints; i += iFreqRatio) {              // HSB:134-140
-        if (i != iSwapTimePoints) P.pay[i] = exp(dStrikeCont * s.dPaymentInterval) - 1;
-        if (i == iSwapTimePoints) P.pay[i] = exp(dStrikeCont * s.dPaymentInterval);
-    }
-    // HJM_Yield_to_Forward (HSB:143): f(0) = y(0), f(i) = (i+1) y(i) - i y(i-1)
-    P.fwd[0] = pdYield[0];
-    for (int i = 1; i <= iN - 1; ++i) P.fwd[i] = (i + 1) * pdYield[i] - i * pdYield[i - 1];
-    // HJM_Drifts (HSB:148): per-factor no-arbitrage drifts, summed over the factors in factor order
-    double drifts[swk::MAXF][swk::MAXN];
-    for (int i = 0; i < iFactors; ++i) {
-        const double *f = ppdFactors + (size_t)i * (iN - 1);
-        drifts[i][0] = 0.5 * ddelt * (f[0]) * (f[0]);
-        for (int j = 1; j <= iN - 2; ++j) {
-            double d = 0;
-            for (int l = 0; l <= j - 1; ++l) d -= drifts[i][l];
-            double dSumVol = 0;
-            for (int l = 0; l <= j; ++l) dSumVol += f[l];
-            d += 0.5 * ddelt * (dSumVol) * (dSumVol);
-            drifts[i][j] = d;
-        }
-        for (int l = 0; l <= iN - 2; ++l) P.fac[i][l] = f[l];
-    }
-    for (int l = 0; l <= iN - 2; ++l) {
-        double tot = 0;
-        for (int i = 0; i < iFactors; ++i) tot += drifts[i][l];
-        P.driftdt[l] = tot * ddelt;  // the product inside HJM_SimPath_Forward_Blocking's path update
-    }
-    P.ddelt = ddelt;
-    P.sqrt_ddelt = sqrt(ddelt);
-    P.swap_ddelt = (double)(dSwapVectorYears / iSwapVectorLength);
-    P.seed = seed;
-    P.trials = lTrials;
-    P.sims = lTrials <= 0 ? 0 : ((lTrials + BLOCKSIZE - 1) / BLOCKSIZE) * (long long)BLOCKSIZE;   // HSB:156
-    P.start = iSwapStartTimeIndex;
-    P.len = iSwapVectorLength;
-    P.last_pay = iSwapTimePoints;
-    return true;
-}
 
 enum Kind { K_FAST = 0, K_LEAN = 1, K_GENERIC = 2 };
 
@@ -313,7 +252,7 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
 
         // this shard's parameter records are prepared while the devices before it already simulate
         for (int i = d.first; i < d.first + d.count; ++i) {
-            if (!prepare(c->h_params[i], swaptions[i], iN, nF, pdYield + (size_t)i * iN, ppdFactors + (size_t)i * nF * (iN - 1),
+            if (!swk::prepare(c->h_params[i], swaptions[i], iN, nF, pdYield + (size_t)i * iN, ppdFactors + (size_t)i * nF * (iN - 1),
                          swaption_seed + i, lTrials, BLOCKSIZE)) {
                 for (int h = 0; h < g; ++h) {  // let what was launched finish before reporting
                     if (cudaSetDevice(c->devs[h].device) == cudaSuccess) cudaStreamSynchronize(c->devs[h].stream);
@@ -378,21 +317,8 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
             for (int i = 0; i < d.count; ++i) {
                 const swk::SwParams &H = c->h_params[d.first + i];
                 swk::OneSwaption P;
-                memset(&P, 0, sizeof(P));
-                for (int l = 0; l < swk::FN - 1; ++l)
-                    P.fd[l] = make_double4(H.fac[0][l] * H.sqrt_ddelt, H.fac[1][l] * H.sqrt_ddelt, H.fac[2][l] * H.sqrt_ddelt, H.driftdt[l]);
-                for (int l = 0; l < swk::FN; ++l) {
-                    P.fwd[l] = H.fwd[l];
-                    P.pay[l] = H.pay[l];
-                }
-                P.ddelt = H.ddelt;
-                P.swap_ddelt = H.swap_ddelt;
-                P.seed = H.seed;
-                P.sims = H.sims;
+                swk::to_one_swaption(P, H);
                 P.chunk_trials = geo.chunk_trials;
-                P.start = H.start;
-                P.len = H.len;
-                P.last_pay = H.last_pay;
                 P.tpt = tpt;
                 P.chunks = geo.chunks;
                 P.partial_base = i * geo.chunks;

@@ -36,7 +36,37 @@
 #include "bs_math_f64.h"
 #include "sw_tail.h"
 
+// The per-trial arithmetic below is host-or-device source, like bs_math_f64.h: nvcc builds the device code; a plain C++
+// compiler (g++ -ffp-contract=off, MUFU seeds emulated) builds the same functions for tools/sw_fast_host_check.cpp, which
+// the CPU tests run against the oracle.  Kernels and warp-level code exist under nvcc only.
+#if defined(__CUDACC__)
+#define SW_HD __device__ __forceinline__
+#define SW_HD_NOINLINE __device__ __noinline__
+#define SW_CONST static __device__ __constant__
+#define SW_HOST_DEVICE __host__ __device__
+#else
+#include <algorithm>
+#define SW_HD inline
+#define SW_HD_NOINLINE inline
+#define SW_CONST static const
+#define SW_HOST_DEVICE
+#endif
+
 namespace swk {
+
+#if defined(__CUDACC__)
+SW_HD int ffs32(uint32_t v) { return __ffs((int)v); }
+SW_HD uint32_t umax32(uint32_t a, uint32_t b) { return max(a, b); }
+SW_HD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+SW_HD double add_rn(double a, double b) { return __dadd_rn(a, b); }
+SW_HD double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+#else
+SW_HD int ffs32(uint32_t v) { return __builtin_ffs((int)v); }
+SW_HD uint32_t umax32(uint32_t a, uint32_t b) { return std::max(a, b); }
+SW_HD double mul_rn(double a, double b) { return a * b; }  // no contraction: the host build uses -ffp-contract=off
+SW_HD double add_rn(double a, double b) { return a + b; }
+SW_HD double div_rn(double a, double b) { return a / b; }
+#endif
 
 constexpr int MAXN = 32;  // SW_GPU_MAX_N
 constexpr int MAXF = 8;   // SW_GPU_MAX_FACTORS
@@ -71,7 +101,7 @@ struct Geom {
 };
 
 // ---- RanUnif (PARSEC RanUnif.c as restated in oracle/sw_absent/sw_leaves.c), literal 64-bit arithmetic ----------
-__device__ __forceinline__ double ranunif_literal(long long ctr)
+SW_HD double ranunif_literal(long long ctr)
 {
     long long ix = ctr;
     ix *= 1513517LL;
@@ -86,20 +116,20 @@ __device__ __forceinline__ double ranunif_literal(long long ctr)
 // +1513517 per draw, and Schrage's step 16807 x mod (2^31 - 1) (exactly what the k1/127773/2836 dance computes
 // for x in [0, 2^31 - 1)) done with one 64-bit product and a Mersenne fold.
 constexpr uint32_t RU_M = 2147483647u;
-__device__ __forceinline__ uint32_t mersenne31(uint64_t p)  // p < 2^62
+SW_HD uint32_t mersenne31(uint64_t p)  // p < 2^62
 {
     uint64_t s = (p & RU_M) + (p >> 31);
     s = (s & RU_M) + (s >> 31);
     uint32_t r = (uint32_t)s;
     return r >= RU_M ? r - RU_M : r;
 }
-__device__ __forceinline__ uint32_t ru_residue(long long ctr) { return mersenne31((uint64_t)ctr * 1513517ull); }
-__device__ __forceinline__ uint32_t ru_next(uint32_t x)
+SW_HD uint32_t ru_residue(long long ctr) { return mersenne31((uint64_t)ctr * 1513517ull); }
+SW_HD uint32_t ru_next(uint32_t x)
 {
     x += 1513517u;
     return x >= RU_M ? x - RU_M : x;
 }
-__device__ __forceinline__ uint32_t ru_int(uint32_t x)  // the 31-bit integer of the draw; u = ru_int * 4.656612875e-10
+SW_HD uint32_t ru_int(uint32_t x)  // the 31-bit integer of the draw; u = ru_int * 4.656612875e-10
 {
     uint64_t p = (uint64_t)x * 16807ull;  // < 2^46
     uint32_t s = (uint32_t)(p & RU_M) + (uint32_t)(p >> 31);
@@ -108,17 +138,15 @@ __device__ __forceinline__ uint32_t ru_int(uint32_t x)  // the 31-bit integer of
 
 // Moro's coefficients; deliberately not const (see bs_tables_f64.h: const __constant__ doubles come back as
 // 64-bit immediates that cost two UMOVs per use).
-static __device__ __constant__ double MORO_A[4] = {2.50662823884, -18.61500062529, 41.39119773534, -25.44106049637};
-static __device__ __constant__ double MORO_B[4] = {-8.47351093090, 23.08336743743, -21.06224101826, 3.13082909833};
-static __device__ __constant__ double MORO_C[9] = {0.3374754822726147, 0.9761690190917186, 0.1607979714918209,
+SW_CONST double MORO_A[4] = {2.50662823884, -18.61500062529, 41.39119773534, -25.44106049637};
+SW_CONST double MORO_B[4] = {-8.47351093090, 23.08336743743, -21.06224101826, 3.13082909833};
+SW_CONST double MORO_C[9] = {0.3374754822726147, 0.9761690190917186, 0.1607979714918209,
                                                    0.0276438810333863, 0.0038405729373609, 0.0003951896511919,
                                                    0.0000321767881768, 0.0000002888167364, 0.0000003960315187};
 
 // ---- CumNormalInv in the reference's operation order, every operation rounded on its own --------------------------
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
-__device__ __noinline__ double cumnormalinv_ieee(double u)
+SW_HD_NOINLINE double cumnormalinv_ieee(double u)
 {
     double x = add_rn(u, -0.5);
     if (fabs(x) < 0.42) {
@@ -127,7 +155,7 @@ __device__ __noinline__ double cumnormalinv_ieee(double u)
         double den = add_rn(
             mul_rn(add_rn(mul_rn(add_rn(mul_rn(add_rn(mul_rn(MORO_B[3], r), MORO_B[2]), r), MORO_B[1]), r), MORO_B[0]), r),
             1.0);
-        return __ddiv_rn(mul_rn(x, num), den);
+        return div_rn(mul_rn(x, num), den);
     }
     double r = u;
     if (x > 0.0) r = add_rn(1.0, -u);
@@ -142,8 +170,8 @@ __device__ __noinline__ double cumnormalinv_ieee(double u)
 // |x| < 700; everything else (huge rates, inf, NaN -- reached only after a draw of exactly 0, see the tail pass) goes
 // to libdevice, out of line.  The range check is done on the high word with integer instructions: the FP64 pipe is
 // the bottleneck of this kernel and a DSETP would cost it two issue cycles per exponential.
-__device__ __noinline__ double exp_slow(double x) { return exp(x); }
-__device__ __forceinline__ double exp_core(double x, const double *tab)
+SW_HD_NOINLINE double exp_slow(double x) { return exp(x); }
+SW_HD double exp_core(double x, const double *tab)
 {
     using namespace bsm;
     const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
@@ -164,9 +192,9 @@ __device__ __forceinline__ double exp_core(double x, const double *tab)
 // exponential with exp_core, branch-free, and only tracks the largest such high word of the trial (LOP3 + VIMNMX on the
 // integer pipes); a trial that exceeded the limit is redone by generic_trial().
 constexpr uint32_t EXP_HI_LIMIT = 0x4085E000u;
-__device__ __forceinline__ double exp_tracked(double x, const double *tab, uint32_t &worst)
+SW_HD double exp_tracked(double x, const double *tab, uint32_t &worst)
 {
-    worst = max(worst, (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu);
+    worst = umax32(worst, (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu);
     return exp_core(x, tab);
 }
 
@@ -178,7 +206,7 @@ constexpr uint32_t S_LO = 171798692u, S_HI = 1975684955u;
 // CumNormalInv's tail branch for draw k of the trial whose first residue is x0, branch-free so that several of them can
 // be interleaved: z = -/+ P8(log(-log(min(u, 1 - u)))).  A draw of exactly 0 (counter a multiple of 2^31 - 1) gives
 // log(-log(0)) = +inf in the reference, hence z = -inf.
-__device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *tab, const double *tailtab)
+SW_HD double tail_normal(uint32_t x0, int k, const double *tab, const double *tailtab)
 {
     uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
     xk = xk >= RU_M ? xk - RU_M : xk;
@@ -203,8 +231,9 @@ __device__ __forceinline__ double tail_normal(uint32_t x0, int k, const double *
     return upper ? p : -p;
 }
 
+#if defined(__CUDACC__)
 // Block-wide sum of two doubles; result valid in thread 0.
-__device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[THREADS / 32])
+SW_HD void block_sum2(double &a, double &b, double (*red)[THREADS / 32])
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -227,6 +256,7 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[T
         }
     }
 }
+#endif  // __CUDACC__
 
 // =====================================================================================================================
 // One trial in the reference's operation order: libdevice exp/log, IEEE divide, every operation rounded on its own
@@ -234,7 +264,7 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[T
 // out-of-line fallback of sw_sim_fast for trials whose exponentials leave the range of its fast arithmetic.
 // Returns the discounted payoff of trial t (HSB:198).
 // =====================================================================================================================
-__device__ __noinline__ double generic_trial(const SwParams &P, int iN, int nF, long long t)
+SW_HD_NOINLINE double generic_trial(const SwParams &P, int iN, int nF, long long t)
 {
     long long ctr = P.seed + t * ((long long)(iN - 1) * nF);
     double row[MAXN], srow[MAXN], z[MAXF];
@@ -282,7 +312,7 @@ struct FastShared {
 // Behind FastShared in dynamic shared memory: z[z_rows][THREADS], the trial's normals [draw][thread] (conflict-free) --
 // all 30 draws for the full kernel, 3 x (largest swap start index of the launch) for the lean one.
 static_assert(sizeof(FastShared) % 16 == 0, "z starts 16-byte aligned");
-__host__ __device__ constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(FastShared) + (size_t)z_rows * THREADS * sizeof(double); }
+SW_HOST_DEVICE constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(FastShared) + (size_t)z_rows * THREADS * sizeof(double); }
 
 // ---- phase A + tail pass -----------------------------------------------------------------------------------------------
 // The trial's normals into sh.z[draw][tid].  Central branch of CumNormalInv for every draw, G draws at a time written stage
@@ -304,7 +334,7 @@ __host__ __device__ constexpr size_t fast_shared_bytes(int z_rows) { return size
 constexpr int TAIL_TRIP = SW_TAIL_TRIP;
 
 template <bool LEAN>
-__device__ __forceinline__ void normals(const double *__restrict__ tab, const double *__restrict__ tailtab, double *__restrict__ z, int tid, uint32_t x0,
+SW_HD void normals(const double *__restrict__ tab, const double *__restrict__ tailtab, double *__restrict__ z, int tid, uint32_t x0,
                                         int steps)
 {
     constexpr int G = LEAN ? FF : SW_PHASE_A_GROUP;
@@ -359,7 +389,7 @@ __device__ __forceinline__ void normals(const double *__restrict__ tab, const do
         }
     }
     while (tail) {
-        const int k0 = __ffs(tail) - 1;
+        const int k0 = ffs32(tail) - 1;
         tail &= tail - 1;
         if (LEAN) {  // three or six draws per trial: rarely more than one tail draw per lane (two per trip measured 8 % slower)
             z[k0 * THREADS + tid] = tail_normal(x0, k0, tab, tailtab);
@@ -370,7 +400,7 @@ __device__ __forceinline__ void normals(const double *__restrict__ tab, const do
             kk[0] = k0;
 #pragma unroll
             for (int i = 1; i < TAIL_TRIP; ++i) {
-                kk[i] = tail ? __ffs(tail) - 1 : k0;
+                kk[i] = tail ? ffs32(tail) - 1 : k0;
                 tail &= tail - 1;  // (0 & anything == 0)
             }
 #pragma unroll
@@ -390,7 +420,7 @@ __device__ __forceinline__ void normals(const double *__restrict__ tab, const do
 // SRC = where the swaption's tables (fd, fwd, pay) are read from: FastShared (shared memory, any swaption per work item)
 // or OneSwaption (kernel-parameter constant bank, one swaption per launch).
 template <bool LEAN, int START, class SRC>
-__device__ __forceinline__ double path_and_payoff(const SRC &sh, const double *__restrict__ tab, const double *__restrict__ z, int tid, double ddelt,
+SW_HD double path_and_payoff(const SRC &sh, const double *__restrict__ tab, const double *__restrict__ z, int tid, double ddelt,
                                                   double swap_ddelt, int start_rt, int swap_end, uint32_t &worst)
 {
     const int start = START >= 0 ? START : start_rt;
@@ -450,6 +480,7 @@ __device__ __forceinline__ double path_and_payoff(const SRC &sh, const double *_
 #ifndef SW_LEAN_MINB
 #define SW_LEAN_MINB 5  /* lean kernel: 5 CTAs per SM (96 registers) measured best: 46.6 / 48.7 / 45.9 G trials/s for 4 / 5 / 8 */
 #endif
+#if defined(__CUDACC__)
 template <bool LEAN>
 __global__ void __launch_bounds__(THREADS, LEAN ? SW_LEAN_MINB : 4)
 sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
@@ -521,6 +552,7 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
         if (tid == 0) partials[item] = make_double2(sum, sumsq);
     }
 }
+#endif  // __CUDACC__
 
 // =====================================================================================================================
 // sw_sim_one: the same trial code for ONE swaption per launch, its tables in the kernel-parameter constant bank.
@@ -545,8 +577,9 @@ struct OneShared {
     double red[2][THREADS / 32];
 };
 static_assert(sizeof(OneShared) % 16 == 0, "z starts 16-byte aligned");
-__host__ __device__ constexpr size_t one_shared_bytes(int z_rows) { return sizeof(OneShared) + (size_t)z_rows * THREADS * sizeof(double); }
+SW_HOST_DEVICE constexpr size_t one_shared_bytes(int z_rows) { return sizeof(OneShared) + (size_t)z_rows * THREADS * sizeof(double); }
 
+#if defined(__CUDACC__)
 template <bool LEAN>
 __global__ void __launch_bounds__(THREADS, LEAN ? SW_LEAN_MINB : 4)
 sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ params, double2 *__restrict__ partials)
@@ -630,5 +663,7 @@ sw_finalize(const SwParams *__restrict__ params, const Geom g, const double2 *__
         err[sw] = __ddiv_rn(__dsqrt_rn(var), __dsqrt_rn(n));
     }
 }
+
+#endif  // __CUDACC__
 
 }  // namespace swk

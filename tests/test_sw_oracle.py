@@ -170,3 +170,70 @@ def test_tail_table_matches_long_double_libm(tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tools", "sw_tail_host_check.cpp"), "-lm"], check=True)
     out = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
     assert float(out["max_rel"]) < 5e-16 and float(out["max_ulp"]) <= 2.5
+
+
+# ---- the fast kernels' per-trial arithmetic, built for the host from the SAME source (sw_kernels.cuh is host-or-device) ----
+@pytest.fixture(scope="module")
+def fast_host(tmp_path_factory):
+    import subprocess
+    root = os.path.join(os.path.dirname(GOLDEN), "..")
+    exe = str(tmp_path_factory.mktemp("swfast") / "sw_fast_host_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-w", "-I/usr/local/cuda/include", "-o", exe,
+                    os.path.join(root, "tools", "sw_fast_host_check.cpp"), "-lm"], check=True)
+
+    def run(p, y, f, seed, trials, lean, source, block_size=16):
+        lines = ["%d %d %d %d %d %d" % (len(p), trials, block_size, seed, lean, source)]
+        for i in range(len(p)):
+            lines.append(" ".join("%.17g" % p[k][i] for k in ("dStrike", "dCompounding", "dMaturity", "dTenor", "dPaymentInterval", "dYears")))
+            lines.append(" ".join("%.17g" % v for v in np.asarray(y[i]).ravel()))
+            lines.append(" ".join("%.17g" % v for v in np.asarray(f[i]).ravel()))
+        out = subprocess.run([exe], input="\n".join(lines), capture_output=True, text=True, check=True).stdout
+        rows = np.array([[float(x) for x in l.split()] for l in out.splitlines() if l.strip()])
+        return rows[:, 0], rows[:, 1], rows[:, 2].astype(int)
+    return run
+
+
+def _close(mean, omean, rtol=1e-12):
+    assert np.array_equal(np.isnan(mean), np.isnan(omean))
+    m = np.isfinite(omean)
+    assert np.array_equal(mean[~m & ~np.isnan(omean)], omean[~m & ~np.isnan(omean)])
+    assert (np.abs(mean[m] - omean[m]) <= rtol * np.abs(omean[m]) + 1e-15).all(), np.abs(mean[m] - omean[m]).max()
+
+
+@pytest.mark.parametrize("lean", [0, 1])
+@pytest.mark.parametrize("source", [0, 1])
+def test_fast_arithmetic_on_the_host_matches_the_oracle(fast_host, lean, source):
+    """normals() + path_and_payoff() + exp_core + the tail table exactly as the GPU kernels compile them (tables from the
+    shared-memory block or from the constant-bank record), summed in trial order: within 1e-12 of the oracle's price."""
+    seed, p, y, f = sw.make_portfolio(12)
+    for trials in (4096, 1003):
+        omean, _ = so.price_map(p, y, f, seed, trials)
+        s, s2, fb = fast_host(p, y, f, seed, trials, lean, source)
+        assert fb.sum() == 0
+        _close(s / trials, omean)
+
+
+def test_fast_arithmetic_every_start_index_on_the_host(fast_host):
+    n = 11
+    p = np.zeros(n, dtype=sw.SWAPTION_DTYPE)
+    p["dYears"], p["dStrike"], p["dPaymentInterval"] = 11.0, 0.09, 1.0
+    p["dMaturity"] = np.arange(n, dtype=np.float64)
+    p["dTenor"] = np.minimum(3.0, 10.0 - np.arange(n))
+    y = np.tile(0.05 + 0.004 * np.arange(11), (n, 1))
+    f = np.tile(sw.FACTOR_TABLE[None] * 1.5, (n, 1, 1))
+    omean, _ = so.price_map(p, y, f, 4242, 2000)
+    for lean in (0, 1):
+        s, _, fb = fast_host(p, y, f, 4242, 2000, lean, 1)
+        assert fb.sum() == 0
+        _close(s / 2000, omean)
+
+
+def test_fast_arithmetic_falls_back_when_a_draw_is_zero(fast_host):
+    """A counter that is a multiple of 2^31 - 1 draws 0 -> z = -inf -> an exponential leaves the fast range: the trial is
+    redone by generic_trial() (the reference's operation order), and the non-finite sums come out like the oracle's."""
+    _, p, y, f = sw.make_portfolio(4)
+    seed = 2147483647 - 40
+    omean, _ = so.price_map(p, y, f, seed, 64)
+    s, _, fb = fast_host(p, y, f, seed, 64, 0, 0)
+    assert fb.sum() >= 1
+    _close(s / 64, omean)
