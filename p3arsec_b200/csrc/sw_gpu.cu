@@ -38,6 +38,13 @@ enum { AUX_STREAMS = 3 };
 // A swaption gets a kernel launch of its own (tables in the constant bank: sw_sim_one) from this many simulated trials
 // on; below it one kernel walks over all (swaption, chunk) items with the tables in shared memory (sw_sim_fast).
 const long long ONE_SWAPTION_MIN_TRIALS = 262144;
+// tuning knob: SW_GPU_ONE_MIN_TRIALS=<n> in the environment overrides the threshold (read at every call)
+long long one_swaption_min_trials()
+{
+    const char *e = getenv("SW_GPU_ONE_MIN_TRIALS");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? v : ONE_SWAPTION_MIN_TRIALS;
+}
 
 struct Dev {
     int device = 0;
@@ -51,6 +58,7 @@ struct Dev {
     double2 *d_partials = nullptr;
     size_t partial_cap = 0;
     double *d_out = nullptr;  // [mean(max) | err(max)]
+    double *d_tables = nullptr;  // [tail table | exp/log tables], expanded once by sw_fill_tables
     int occ_fast = 0, occ_lean = 0, occ_generic = 0;
     float roi_ms = 0;
 };
@@ -131,6 +139,7 @@ void sw_gpu_fini(sw_gpu_ctx *ctx)
         if (d.d_params) cudaFree(d.d_params);
         if (d.d_partials) cudaFree(d.d_partials);
         if (d.d_out) cudaFree(d.d_out);
+        if (d.d_tables) cudaFree(d.d_tables);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         for (int k = 0; k < AUX_STREAMS; ++k) {
@@ -171,6 +180,10 @@ static int init_impl(sw_gpu_ctx *c, const int *devices, int num_gpus)
         SW_CUDA(c, cudaEventCreate(&d.ev1));
         SW_CUDA(c, cudaMalloc(&d.d_params, n * sizeof(swk::SwParams)));
         SW_CUDA(c, cudaMalloc(&d.d_out, 2 * n * sizeof(double)));
+        SW_CUDA(c, cudaMalloc(&d.d_tables, swk::TABLE_DOUBLES * sizeof(double)));
+        swk::sw_fill_tables<<<1, 128, 0, d.stream>>>(d.d_tables);
+        SW_CUDA(c, cudaGetLastError());
+        SW_CUDA(c, cudaStreamSynchronize(d.stream));
         const size_t full_smem = swk::fast_shared_bytes(swk::FD);
         SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full_smem));
         SW_CUDA(c, cudaFuncSetAttribute(swk::sw_sim_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full_smem));
@@ -264,7 +277,7 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
 
         // shared memory of the fast kernels: the lean one keeps only the draws of the time steps it simulates
         // (full kernel only: a lean launch of one swaption is too short -- 20 us per million trials -- and measured 33 % slower)
-        const bool one = kind == K_FAST && !(flags & SW_GPU_FLAG_BATCHED) && sims >= ONE_SWAPTION_MIN_TRIALS;
+        const bool one = kind == K_FAST && !(flags & SW_GPU_FLAG_BATCHED) && sims >= one_swaption_min_trials();
         int z_rows = swk::FD;
         if (kind == K_LEAN) {
             int max_start = 1;
@@ -324,8 +337,8 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
                 P.partial_base = i * geo.chunks;
                 P.sw_index = i;
                 cudaStream_t st = (i % (AUX_STREAMS + 1)) == 0 ? d.stream : d.aux[(i % (AUX_STREAMS + 1)) - 1];
-                if (kind == K_FAST) swk::sw_sim_one<false><<<blocks, swk::THREADS, smem, st>>>(P, d.d_params, d.d_partials);
-                else swk::sw_sim_one<true><<<blocks, swk::THREADS, smem, st>>>(P, d.d_params, d.d_partials);
+                if (kind == K_FAST) swk::sw_sim_one<false><<<blocks, swk::THREADS, smem, st>>>(P, d.d_params, d.d_partials, d.d_tables);
+                else swk::sw_sim_one<true><<<blocks, swk::THREADS, smem, st>>>(P, d.d_params, d.d_partials, d.d_tables);
             }
             SW_CUDA(c, cudaGetLastError());
             for (int k = 0; k < AUX_STREAMS; ++k) {
@@ -334,9 +347,9 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
             }
             c->timing.kernel_launches += (unsigned long long)d.count - 1;
         } else if (kind == K_FAST)
-            swk::sw_sim_fast<false><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials);
+            swk::sw_sim_fast<false><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials, d.d_tables);
         else if (kind == K_LEAN)
-            swk::sw_sim_fast<true><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials);
+            swk::sw_sim_fast<true><<<blocks, swk::THREADS, smem, d.stream>>>(d.d_params, geo, d.d_partials, d.d_tables);
         else
             swk::sw_sim_generic<<<blocks, swk::THREADS, 0, d.stream>>>(d.d_params, geo, d.d_partials);
         SW_CUDA(c, cudaGetLastError());

@@ -31,6 +31,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "bs_math_f64.h"
@@ -232,6 +233,21 @@ SW_HD double tail_normal(uint32_t x0, int k, const double *tab, const double *ta
 }
 
 #if defined(__CUDACC__)
+// The exp/log tables and the tail table, [tail | tab], as the kernels' shared-memory blocks start with them.  They are
+// expanded once per device into global memory by sw_fill_tables; every CTA then copies them with coalesced loads (the
+// per-thread-indexed reads of the __constant__ originals serialise in the constant cache: ~10 us per launch, which is
+// what a one-swaption launch or a small portfolio cannot afford).
+constexpr int TABLE_DOUBLES = swt::TAIL_DOUBLES + bsm::TAB_DOUBLES;
+__global__ void sw_fill_tables(double *__restrict__ g)
+{
+    swt::fill_tail(g, threadIdx.x, blockDim.x);
+    bsm::fill_tables(g + swt::TAIL_DOUBLES, threadIdx.x, blockDim.x);
+}
+SW_HD void load_tables(double *__restrict__ smem_tail_then_tab, const double *__restrict__ g, int tid)
+{
+    for (int i = tid; i < TABLE_DOUBLES; i += THREADS) smem_tail_then_tab[i] = g[i];
+}
+
 // Block-wide sum of two doubles; result valid in thread 0.
 SW_HD void block_sum2(double &a, double &b, double (*red)[THREADS / 32])
 {
@@ -483,14 +499,14 @@ SW_HD double path_and_payoff(const SRC &sh, const double *__restrict__ tab, cons
 #if defined(__CUDACC__)
 template <bool LEAN>
 __global__ void __launch_bounds__(THREADS, LEAN ? SW_LEAN_MINB : 4)
-sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials)
+sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restrict__ partials, const double *__restrict__ tables)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastShared &sh = *reinterpret_cast<FastShared *>(smem_raw);
     double *const z = reinterpret_cast<double *>(smem_raw + sizeof(FastShared));
     const int tid = threadIdx.x;
-    bsm::fill_tables(sh.tab, tid, THREADS);
-    swt::fill_tail(sh.tail, tid, THREADS);
+    static_assert(offsetof(FastShared, tail) == 0 && offsetof(FastShared, tab) == sizeof(double) * swt::TAIL_DOUBLES, "[tail | tab] first");
+    load_tables(sh.tail, tables, tid);
 
     int cur = -1;
     double ddelt = 0, swap_ddelt = 0;
@@ -582,14 +598,15 @@ SW_HOST_DEVICE constexpr size_t one_shared_bytes(int z_rows) { return sizeof(One
 #if defined(__CUDACC__)
 template <bool LEAN>
 __global__ void __launch_bounds__(THREADS, LEAN ? SW_LEAN_MINB : 4)
-sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ params, double2 *__restrict__ partials)
+sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ params, double2 *__restrict__ partials,
+           const double *__restrict__ tables)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OneShared &sh = *reinterpret_cast<OneShared *>(smem_raw);
     double *const z = reinterpret_cast<double *>(smem_raw + sizeof(OneShared));
     const int tid = threadIdx.x;
-    bsm::fill_tables(sh.tab, tid, THREADS);
-    swt::fill_tail(sh.tail, tid, THREADS);
+    static_assert(offsetof(OneShared, tail) == 0 && offsetof(OneShared, tab) == sizeof(double) * swt::TAIL_DOUBLES, "[tail | tab] first");
+    load_tables(sh.tail, tables, tid);
     const int steps = LEAN ? P.start : FN - 1;
     const int swap_end = LEAN ? P.last_pay : P.len - 1;
 
