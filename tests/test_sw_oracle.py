@@ -237,3 +237,36 @@ def test_fast_arithmetic_falls_back_when_a_draw_is_zero(fast_host):
     s, _, fb = fast_host(p, y, f, seed, 64, 0, 0)
     assert fb.sum() >= 1
     _close(s / 64, omean)
+
+
+@pytest.mark.parametrize("rng_seed", [1, 2, 3])
+def test_fast_arithmetic_random_portfolios_on_the_host(fast_host, rng_seed):
+    """Random contracts beyond what the reference driver creates (compounding conventions, maturities, tenors, payment
+    intervals, per-swaption yield curves and factor tables): the host build of the fast arithmetic against the oracle,
+    full and lean.  Contracts whose time indices leave the path are refused by both (the checker prints 'invalid')."""
+    rng = np.random.RandomState(rng_seed)
+    n = 16
+    p = np.zeros(n, dtype=sw.SWAPTION_DTYPE)
+    p["dYears"] = 5.0 + rng.randint(0, 60, n) * 0.25
+    p["dStrike"] = 0.01 + rng.randint(0, 40, n) * 0.005
+    p["dCompounding"] = rng.choice([0.0, 0.5, 1.0], n)
+    p["dMaturity"] = rng.choice([0.5, 1.0, 2.0, 3.0], n)
+    p["dTenor"] = rng.choice([1.0, 2.0, 3.0, 5.0], n)
+    p["dPaymentInterval"] = rng.choice([0.5, 1.0, 2.0], n)
+    y = 0.02 + 0.1 * rng.rand(n, 1) + np.cumsum(0.004 * rng.rand(n, 11), axis=1)
+    f = sw.FACTOR_TABLE[None] * (0.25 + 2.0 * rng.rand(n, 3, 1)) * np.where(rng.rand(n, 3, 10) < 0.1, -1.0, 1.0)
+    keep = []
+    for i in range(n):
+        try:
+            so.price_map(p[i:i + 1], y[i:i + 1], f[i:i + 1], 1, 16)
+            keep.append(i)
+        except ValueError:
+            pass
+    assert len(keep) >= 6
+    p, y, f = p[keep], y[keep], f[keep]
+    seed = int(rng.randint(0, 2**31 - 1))
+    omean, _ = so.price_map(p, y, f, seed, 1500)
+    for lean in (0, 1):
+        s, _, fb = fast_host(p, y, f, seed, 1500, lean, lean)
+        assert fb.sum() == 0
+        _close(s / 1500, omean)
