@@ -41,7 +41,7 @@ def test_oracle_matches_reference_output_byte_for_byte(name):
 
 
 @pytest.mark.skipif(not so.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
-@pytest.mark.parametrize("binary,nt", [("sw_ref_serial", 1), ("sw_ref_ff", 4)])
+@pytest.mark.parametrize("binary,nt", [("sw_ref_serial", 1), ("sw_ref_ff", 4), ("sw_ref_skepu", 2)])
 def test_oracle_matches_reference_run_now(binary, nt):
     if not so.have_ref(binary):
         pytest.skip(binary + " not built")
