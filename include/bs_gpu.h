@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BS_GPU_ABI_VERSION 1
+#define BS_GPU_ABI_VERSION 2
 
 typedef struct bs_gpu_ctx bs_gpu_ctx;
 
@@ -66,13 +66,30 @@ typedef enum bs_gpu_buffer {
     BS_BUF_COUNT = 8
 } bs_gpu_buffer;
 
-/* How exp/log/sqrt/divide are evaluated by the fp32 kernel (fp64 always uses IEEE operations in the
- * reference's operation order).  Both stay inside the reference's own ERR_CHK band (1e-4); the
- * measured distance to the reference CPU output is in DESIGN.md. */
+/* How exp/log/sqrt/divide are evaluated.  BS_MATH_DEFAULT resolves to BS_MATH_FAST for BOTH precisions -- this
+ * is what bs_gpu_init() (the entry the reference patch calls) uses; ask for BS_MATH_IEEE or BS_MATH_REFERENCE
+ * through bs_gpu_init_ex() to get the reference's operation order.
+ *
+ * Accuracy contract (measured worst cases: DESIGN.md section 4 and profiles/r02_fp32_adversarial.json):
+ *   fp32, operands in the PARSEC inputgen range (spot, strike <= 128; 0.05 <= v <= 0.65; 0.05 <= t <= 1):
+ *         every mode: |price - reference CPU price| <= 1e-4, the reference's own ERR_CHK threshold
+ *         (blackscholes.c:335).  BS_MATH_REFERENCE is typically bit-identical (worst measured distance in DESIGN.md).
+ *   fp32, larger operands: BS_MATH_REFERENCE keeps the flat 1e-4 bound; BS_MATH_FAST / BS_MATH_IEEE keep the same
+ *         number of ulps, i.e. the bound scales as 1e-4 * max(1, max(spot, strike) / 128): a price near 1000 is
+ *         itself quantised to 6e-5 in fp32 and the reference's own fp32 build is 1.7e-4 from its fp64 build there.
+ *   fp64: |delta| <= 1e-9 * |reference| + 1e-12 in every mode (FAST: ~2 ulp building blocks; IEEE: only the last
+ *         ulp of exp()/log() can differ from the fp64 CPU build). */
 typedef enum bs_gpu_math {
-    BS_MATH_DEFAULT = 0, /* the library's default (currently BS_MATH_FAST)             */
-    BS_MATH_IEEE = 1,    /* expf/logf/sqrtf and IEEE-rounded divides, reference operation order       */
-    BS_MATH_FAST = 2     /* MUFU ex2/lg2/rsq/rcp with folded constants, Horner CNDF, branch-free      */
+    BS_MATH_DEFAULT = 0,  /* the library's default: BS_MATH_FAST (fp32 and fp64)                                  */
+    BS_MATH_IEEE = 1,     /* libdevice exp/log/sqrt and IEEE-rounded divides, reference operation order; fp32 is
+                             pure fp32 (the reference's double-literal promotions are not imitated)               */
+    BS_MATH_FAST = 2,     /* fp32: MUFU ex2/lg2/sqrt/rcp with folded constants, Horner CNDF, branch-free;
+                             fp64: table-driven exp/log, MUFU-seeded reciprocals (bs_math_f64.h), with the IEEE
+                             path taken for operands outside its range (t = 0, v = 0, denormals, overflow)       */
+    BS_MATH_REFERENCE = 3 /* fp32: the reference's fp32 build as compiled -- same operation order AND its double
+                             promotions (blackscholes.c:154-158,164-175,232,252-253), every operation individually
+                             rounded, expf/logf correctly rounded from fp64.  The validation mode: several times
+                             slower than FAST.  fp64: identical to BS_MATH_IEEE (nothing is promoted)             */
 } bs_gpu_math;
 
 /* bs_gpu_config.flags */
@@ -96,12 +113,14 @@ typedef struct bs_gpu_config {
     const int *devices;  /* G CUDA device ordinals, or NULL for 0..G-1                                */
     unsigned flags;      /* BS_GPU_FLAG_*                                                            */
     int math;            /* bs_gpu_math                                                              */
-    int threads_per_block; /* 0 = default; else 64..256, multiple of 32                              */
+    int threads_per_block; /* 0 = default; else 32..256, multiple of 32                              */
     int blocks_per_sm;     /* 0 = default (all the CTAs the SM can hold)                             */
     int unroll;            /* 0 = default; else 1, 2 or 4 independent 16-byte groups per thread-trip */
     int variant;           /* 0 = default; bit 0: software-pipelined loads; bit 1: DIAGNOSTIC traffic probe
                               (no pricing, same streams); bit 2: TMA variant (inputs moved by cp.async.bulk
-                              into a shared-memory ring) -- see DESIGN.md                                */
+                              into a shared-memory ring) -- see DESIGN.md; bit 3: DIAGNOSTIC fault injection
+                              (every Map launch requests 1 MiB of shared memory and is rejected by the runtime:
+                              the calls must then return BS_GPU_ERR_CUDA with text, never prices)             */
 } bs_gpu_config;
 
 typedef struct bs_gpu_timing {
@@ -160,6 +179,17 @@ int bs_gpu_price(bs_gpu_ctx *ctx, int num_runs, int err_chk, unsigned long long 
 int bs_gpu_upload(bs_gpu_ctx *ctx);
 int bs_gpu_run(bs_gpu_ctx *ctx, int num_runs, int err_chk, unsigned long long *num_errors);
 int bs_gpu_download(bs_gpu_ctx *ctx);
+
+/* The CAF Map's entry point (blackscholes.c:482-570, driver :771-778,:874-885): the reference's CAF_V3 build sends
+ * its actors ONE message holding the options as an array of
+ *     struct DataCont { int otype; float sptprice, strike, rate, volatility, otime; };      (24 bytes, :482-489)
+ * and receives a vector of prices (OutVec, :492).  `records` points at `num_records` such records in ordinary
+ * (pageable) host memory -- e.g. data_vec.data() -- and must equal the context's num_options; the context must have
+ * fp_bytes = 4.  The records are copied H2D as they are and gathered into the SoA streams on the device, then
+ * `num_runs` real launches, then the prices are copied into out_prices[0..num_records).  Shards over several GPUs
+ * exactly like bs_gpu_price().  (The reference's message holds 2N records, the first N zero-initialised, :772-777;
+ * a caller that reproduces that passes num_records = 2N and gets NaN for the zero records, as the reference does.) */
+int bs_gpu_price_aos(bs_gpu_ctx *ctx, const void *records, size_t num_records, float *out_prices, int num_runs);
 
 /* Fill the DEVICE input streams (and DGREFVAL when allocated) with the synthetic inputgen sequence:
  * global option i = table[(first_index + i) % 1000] (p3arsec_b200/csrc/bs_option_table.h).  Used for

@@ -39,7 +39,7 @@
 
 namespace {
 
-enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_PIN, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_PRICE, CMD_FILL, CMD_TEARDOWN, CMD_EXIT };
+enum Cmd { CMD_NONE = 0, CMD_SETUP, CMD_PIN, CMD_UPLOAD, CMD_RUN, CMD_DOWNLOAD, CMD_PRICE, CMD_FILL, CMD_AOS_IN, CMD_DOWNLOAD_TO, CMD_TEARDOWN, CMD_EXIT };
 
 enum { PIPE_CHUNKS = 8 };  // chunks of the first / last run of a pipelined bs_gpu_price()
 
@@ -68,6 +68,8 @@ struct Shard {
     unsigned int *d_list_count = nullptr;
     long long *d_list = nullptr;
     char *d_table = nullptr;  // synthetic base table, built on first fill
+    char *d_aos = nullptr;    // CAF DataCont records of the shard (bs_gpu_price_aos), allocated on first use
+    size_t d_aos_bytes = 0;
     // execution
     cudaStream_t stream = nullptr;       // launches (and the un-pipelined copies)
     cudaStream_t copy_stream = nullptr;  // H2D (and, in the chunked scheme, D2H) of a pipelined bs_gpu_price()
@@ -120,6 +122,8 @@ struct bs_gpu_ctx {
     // command arguments
     int arg_num_runs = 0, arg_err_chk = 0, arg_upload_what = 0;
     unsigned long long arg_first_index = 0;
+    const void *arg_aos = nullptr;  // bs_gpu_price_aos: the caller's record array
+    void *arg_out = nullptr;        // bs_gpu_price_aos: the caller's price array
     // reporting
     bs_gpu_timing timing;
     std::string err;
@@ -161,8 +165,10 @@ enum {
     VARIANT_PIPE = 1,   // software-pipelined loads (next trip in flight during the math)
     VARIANT_PROBE = 2,  // DIAGNOSTIC ONLY: no pricing, same seven streams (sum of the inputs is written): the
                         // bandwidth ceiling of this traffic pattern.  Never selected by default.
-    VARIANT_TMA = 4     // inputs moved by cp.async.bulk into a shared-memory ring (bs_map_tma); ERR_CHK runs use
+    VARIANT_TMA = 4,    // inputs moved by cp.async.bulk into a shared-memory ring (bs_map_tma); ERR_CHK runs use
                         // the plain kernel
+    VARIANT_FAULT = 8   // DIAGNOSTIC ONLY (fault injection for the tests): every Map launch asks for 1 MiB of dynamic
+                        // shared memory, which the runtime rejects -- proves a failed launch surfaces as BS_GPU_ERR_CUDA
 };
 
 template <typename FP, int MATH, bool CHK, bool PIPE>
@@ -178,6 +184,8 @@ template <typename FP>
 void (*pick_kernel(int math, int unroll, bool chk, bool pipe))(bsk::Streams<FP>, size_t, bsk::ErrChk)
 {
     if (math == bsk::MATH_PROBE) return unroll == 1 ? bsk::bs_map<FP, bsk::MATH_PROBE, 1, false, false> : bsk::bs_map<FP, bsk::MATH_PROBE, 2, false, false>;
+    if (math == BS_MATH_REFERENCE)  // validation mode: one geometry (one group per trip, plain loads)
+        return chk ? bsk::bs_map<FP, bsk::MATH_REFERENCE, 1, true, false> : bsk::bs_map<FP, bsk::MATH_REFERENCE, 1, false, false>;
     if (math == BS_MATH_IEEE) {
         if (chk) return pipe ? pick_unroll<FP, bsk::MATH_IEEE, true, true>(unroll) : pick_unroll<FP, bsk::MATH_IEEE, true, false>(unroll);
         return pipe ? pick_unroll<FP, bsk::MATH_IEEE, false, true>(unroll) : pick_unroll<FP, bsk::MATH_IEEE, false, false>(unroll);
@@ -185,8 +193,13 @@ void (*pick_kernel(int math, int unroll, bool chk, bool pipe))(bsk::Streams<FP>,
     if (chk) return pipe ? pick_unroll<FP, bsk::MATH_FAST, true, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, true, false>(unroll);
     return pipe ? pick_unroll<FP, bsk::MATH_FAST, false, true>(unroll) : pick_unroll<FP, bsk::MATH_FAST, false, false>(unroll);
 }
-int kernel_math(const bs_gpu_ctx *c) { return (c->variant & VARIANT_PROBE) ? (int)bsk::MATH_PROBE : c->math; }
-bool use_tma(const bs_gpu_ctx *c, bool chk) { return (c->variant & VARIANT_TMA) && !chk; }
+int kernel_math(const bs_gpu_ctx *c)
+{
+    if (c->variant & VARIANT_PROBE) return (int)bsk::MATH_PROBE;
+    if (c->math == BS_MATH_REFERENCE && c->fp_bytes == 8) return BS_MATH_IEEE;  // fptype=double: nothing is promoted
+    return c->math;
+}
+bool use_tma(const bs_gpu_ctx *c, bool chk) { return (c->variant & VARIANT_TMA) && !chk && c->math != BS_MATH_REFERENCE; }
 template <typename FP> const void *tma_kernel(int math)
 {
     if (math == bsk::MATH_PROBE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_PROBE>;
@@ -206,9 +219,10 @@ const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
 // programmatic-stream-serialization attribute: behind another Map launch it may begin (and issue its first loads)
 // while that one drains; the kernel itself orders its stores after the predecessor (griddepcontrol.wait).  Behind
 // a copy or memset the attribute has no effect.  Captured into the runs graph as a programmatic edge.
-void launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *streams, size_t *count, bsk::ErrChk *ec, bool allow_pdl,
-                   int threads = 0, size_t smem = 0)
+cudaError_t launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *streams, size_t *count, bsk::ErrChk *ec, bool allow_pdl,
+                          int threads = 0, size_t smem = 0)
 {
+    if (c->variant & VARIANT_FAULT) smem = (size_t)1 << 20;
     void *args[3] = {streams, count, ec};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)blocks);
@@ -220,13 +234,13 @@ void launch_kernel(bs_gpu_ctx *c, Shard &s, const void *fn, int blocks, void *st
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (allow_pdl && (c->flags & BS_GPU_FLAG_PDL)) ? 1 : 0;
-    cudaLaunchKernelExC(&cfg, fn, args);
+    return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
 // Launch the Map over options [first, first+count) of the shard (first must be a multiple of 4).
-void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t first, size_t count, bool allow_pdl = false)
+cudaError_t launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t first, size_t count, bool allow_pdl = false)
 {
-    if (count == 0) return;
+    if (count == 0) return cudaSuccess;
     bsk::ErrChk ec;
     ec.count = s.d_err_count;
     ec.list_count = s.d_list_count;
@@ -251,8 +265,8 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (float *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const float *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        if (use_tma(c, chk)) launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
-        else launch_kernel(c, s, (const void *)pick_f32(c, chk), blocks, &a, &count, &ec, allow_pdl);
+        if (use_tma(c, chk)) return launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
+        return launch_kernel(c, s, (const void *)pick_f32(c, chk), blocks, &a, &count, &ec, allow_pdl);
     } else {
         bsk::StreamsF64 a;
         a.spt = (const double *)s.d[BS_BUF_SPTPRICE] + first;
@@ -263,8 +277,8 @@ void launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size_t firs
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (double *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        if (use_tma(c, chk)) launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
-        else launch_kernel(c, s, (const void *)pick_f64(c, chk), blocks, &a, &count, &ec, allow_pdl);
+        if (use_tma(c, chk)) return launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
+        return launch_kernel(c, s, (const void *)pick_f64(c, chk), blocks, &a, &count, &ec, allow_pdl);
     }
 }
 
@@ -386,16 +400,21 @@ void do_upload(bs_gpu_ctx *c, Shard &s, int what)
 }
 
 // NUM_RUNS real launches (blackscholes.c:318): every run re-reads all inputs and rewrites all prices
-void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last, size_t first, size_t count)
+cudaError_t enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last, size_t first, size_t count)
 {
-    for (int j = 0; j < num_runs; j++) launch_map_range(c, s, chk, chk && record_last && j == num_runs - 1, first, count, true);
+    for (int j = 0; j < num_runs; j++) {
+        const cudaError_t e = launch_map_range(c, s, chk, chk && record_last && j == num_runs - 1, first, count, true);
+        if (e != cudaSuccess) return e;  // the first failed launch ends the sequence: nothing after it would be valid
+    }
+    return cudaSuccess;
 }
-void enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last) { enqueue_runs(c, s, num_runs, chk, record_last, 0, s.count); }
+cudaError_t enqueue_runs(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool record_last) { return enqueue_runs(c, s, num_runs, chk, record_last, 0, s.count); }
 
-void reset_err_counters(Shard &s)
+cudaError_t reset_err_counters(Shard &s)
 {
-    cudaMemsetAsync(s.d_err_count, 0, sizeof(unsigned long long), s.stream);
-    cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream);
+    const cudaError_t e = cudaMemsetAsync(s.d_err_count, 0, sizeof(unsigned long long), s.stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(s.d_list_count, 0, sizeof(unsigned int), s.stream);
 }
 
 // `num_runs` launches over [first, first+count) as one cached CUDA graph (or nullptr when graphs are disabled)
@@ -407,12 +426,19 @@ cudaGraphExec_t runs_graph(bs_gpu_ctx *c, Shard &s, int num_runs, bool chk, bool
     if (it != s.graphs.end()) return it->second;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return nullptr;
-    enqueue_runs(c, s, num_runs, chk, record_last, first, count);
-    if (cudaStreamEndCapture(s.stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return nullptr; }
+    // Any failure here returns nullptr and the caller launches the runs directly, where the same failure (if it is
+    // one of the launch, not of the capture machinery) is reported with its CUDA error text.
+    if (cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const cudaError_t queued = enqueue_runs(c, s, num_runs, chk, record_last, first, count);
+    const cudaError_t ended = cudaStreamEndCapture(s.stream, &graph);
+    if (queued != cudaSuccess || ended != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return nullptr;
+    }
     if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return nullptr; }
     cudaGraphDestroy(graph);
-    cudaGraphUpload(exec, s.stream);
+    if (cudaGraphUpload(exec, s.stream) != cudaSuccess) cudaGetLastError();  // an optimisation only: the first launch uploads otherwise
     s.graphs[key] = exec;
     return exec;
 }
@@ -430,11 +456,11 @@ void do_run(bs_gpu_ctx *c, Shard &s)
     if (s.count == 0) { s.roi_ms = 0; s.err_total = 0; s.list_n = 0; s.list.clear(); return; }
     cudaGraphExec_t exec = runs_graph(c, s, num_runs, chk, true);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
-    if (chk) reset_err_counters(s);
+    if (chk) SH_CUDA(reset_err_counters(s));
     if (exec) {
         SH_CUDA(cudaGraphLaunch(exec, s.stream));
     } else {
-        enqueue_runs(c, s, num_runs, chk, true);
+        SH_CUDA(enqueue_runs(c, s, num_runs, chk, true));
         SH_CUDA(cudaGetLastError());
     }
     SH_CUDA(cudaEventRecord(s.ev1, s.stream));
@@ -506,7 +532,7 @@ void do_price_subshards(bs_gpu_ctx *c, Shard &s, int S)
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev0, 0));
     SH_CUDA(cudaStreamWaitEvent(s.d2h_stream, s.ev0, 0));
-    if (chk) reset_err_counters(s);
+    if (chk) SH_CUDA(reset_err_counters(s));
     if (what) {
         for (int k = 0; k < S; k++) {
             const size_t n = lo[k + 1] - lo[k];
@@ -530,7 +556,7 @@ void do_price_subshards(bs_gpu_ctx *c, Shard &s, int S)
         if (what) SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_in[k], 0));
         if (k == 0) SH_CUDA(cudaEventRecord(s.ev_k0, s.stream));
         if (exec[k]) SH_CUDA(cudaGraphLaunch(exec[k], s.stream));
-        else enqueue_runs(c, s, R, chk, true, lo[k], lo[k + 1] - lo[k]);
+        else SH_CUDA(enqueue_runs(c, s, R, chk, true, lo[k], lo[k + 1] - lo[k]));
         SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
     }
     SH_CUDA(cudaGetLastError());
@@ -573,7 +599,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
 
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev0, 0));
-    if (chk) reset_err_counters(s);
+    if (chk) SH_CUDA(reset_err_counters(s));
 
     // ---- inputs: chunked H2D on the copy stream
     if (what) {
@@ -601,31 +627,35 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     // ---- runs
     int done = 0;
     bool k0_marked = false;
-    auto mark_k0 = [&]() { if (!k0_marked) { cudaEventRecord(s.ev_k0, s.stream); k0_marked = true; } };
+    auto mark_k0 = [&]() -> cudaError_t {
+        if (k0_marked) return cudaSuccess;
+        k0_marked = true;
+        return cudaEventRecord(s.ev_k0, s.stream);
+    };
     if (R >= 1 && what) {  // run 0 follows the input chunks (it is also the last run when R == 1)
         const bool last = (R == 1);
         for (int k = 0; k < PIPE_CHUNKS; k++) {
             SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_in[k], 0));
-            mark_k0();
-            launch_map_range(c, s, chk, chk && last, lo[k], lo[k + 1] - lo[k]);
+            SH_CUDA(mark_k0());
+            SH_CUDA(launch_map_range(c, s, chk, chk && last, lo[k], lo[k + 1] - lo[k]));
             if (last) SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
         }
         done = 1;
     } else if (what) {
         SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_h2d, 0));  // R == 0: nothing to overlap with
     }
-    mark_k0();
+    SH_CUDA(mark_k0());
     const int middle = std::max(0, R - done - 1);  // whole-shard runs between the pipelined first and last
     if (middle > 0) {
         cudaGraphExec_t exec = runs_graph(c, s, middle, chk, false);
         if (exec) SH_CUDA(cudaGraphLaunch(exec, s.stream));
-        else enqueue_runs(c, s, middle, chk, false);
+        else SH_CUDA(enqueue_runs(c, s, middle, chk, false));
         done += middle;
     }
     bool out_marked = (R == 1 && what);
     if (done < R) {  // the last run, chunk by chunk, each chunk's prices leaving as soon as they exist
         for (int k = 0; k < PIPE_CHUNKS; k++) {
-            launch_map_range(c, s, chk, chk, lo[k], lo[k + 1] - lo[k]);
+            SH_CUDA(launch_map_range(c, s, chk, chk, lo[k], lo[k + 1] - lo[k]));
             SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
         }
         out_marked = true;
@@ -657,6 +687,49 @@ void do_download(bs_gpu_ctx *c, Shard &s)
     const size_t eb = elem_bytes(c, BS_BUF_PRICES);
     SH_CUDA(cudaEventRecord(s.ev0, s.stream));
     SH_CUDA(cudaMemcpyAsync((char *)c->host[BS_BUF_PRICES] + s.first * eb, s.d[BS_BUF_PRICES], s.count * eb, cudaMemcpyDeviceToHost, s.stream));
+    SH_CUDA(cudaEventRecord(s.ev1, s.stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.d2h_ms, s.ev0, s.ev1));
+}
+
+// bs_gpu_price_aos, input half: the shard's slice of the caller's DataCont records (24 bytes each, pageable memory)
+// goes H2D as it is and is turned into the SoA streams on the device (bsk::bs_aos_to_soa).
+void do_aos_in(bs_gpu_ctx *c, Shard &s)
+{
+    s.h2d_ms = 0;
+    if (s.count == 0) return;
+    const size_t rec = sizeof(int) + 5 * sizeof(float);
+    const size_t tiles = (s.count + bsk::AOS_TILE - 1) / bsk::AOS_TILE;
+    const size_t need = tiles * bsk::AOS_TILE * rec;  // whole tiles: the gather reads 16-byte vectors up to the tile end
+    if (s.d_aos_bytes < need) {
+        if (s.d_aos) SH_CUDA(cudaFree(s.d_aos));
+        s.d_aos = nullptr;
+        s.d_aos_bytes = 0;
+        SH_CUDA(cudaMalloc((void **)&s.d_aos, need));
+        s.d_aos_bytes = need;
+    }
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    SH_CUDA(cudaMemcpyAsync(s.d_aos, (const char *)c->arg_aos + s.first * rec, s.count * rec, cudaMemcpyHostToDevice, s.stream));
+    const int blocks = (int)std::min<size_t>(tiles, (size_t)s.sm_count * 8);
+    bsk::bs_aos_to_soa<<<blocks, bsk::AOS_TILE, 0, s.stream>>>((const uint4 *)s.d_aos, s.count, (float *)s.d[BS_BUF_SPTPRICE],
+                                                              (float *)s.d[BS_BUF_STRIKE], (float *)s.d[BS_BUF_RATE],
+                                                              (float *)s.d[BS_BUF_VOLATILITY], (float *)s.d[BS_BUF_OTIME],
+                                                              (int *)s.d[BS_BUF_OTYPE]);
+    SH_CUDA(cudaGetLastError());
+    SH_CUDA(cudaEventRecord(s.ev1, s.stream));
+    SH_CUDA(cudaEventSynchronize(s.ev1));
+    SH_CUDA(cudaEventElapsedTime(&s.h2d_ms, s.ev0, s.ev1));
+    s.refval_on_device = false;
+}
+
+// bs_gpu_price_aos, output half: the shard's prices into the caller's (pageable) array.
+void do_download_to(bs_gpu_ctx *c, Shard &s)
+{
+    s.d2h_ms = 0;
+    if (s.count == 0) return;
+    const size_t eb = elem_bytes(c, BS_BUF_PRICES);
+    SH_CUDA(cudaEventRecord(s.ev0, s.stream));
+    SH_CUDA(cudaMemcpyAsync((char *)c->arg_out + s.first * eb, s.d[BS_BUF_PRICES], s.count * eb, cudaMemcpyDeviceToHost, s.stream));
     SH_CUDA(cudaEventRecord(s.ev1, s.stream));
     SH_CUDA(cudaEventSynchronize(s.ev1));
     SH_CUDA(cudaEventElapsedTime(&s.d2h_ms, s.ev0, s.ev1));
@@ -727,6 +800,9 @@ void do_teardown(bs_gpu_ctx *c, Shard &s)
     for (auto &kv : s.graphs) cudaGraphExecDestroy(kv.second);
     s.graphs.clear();
     if (s.d_table) cudaFree(s.d_table);
+    if (s.d_aos) cudaFree(s.d_aos);
+    s.d_aos = nullptr;
+    s.d_aos_bytes = 0;
     if (s.d_list) cudaFree(s.d_list);
     if (s.d_list_count) cudaFree(s.d_list_count);
     if (s.d_err_count) cudaFree(s.d_err_count);
@@ -769,6 +845,8 @@ void device_thread(bs_gpu_ctx *c, int g)
         case CMD_FILL:
             if (c->fp_bytes == 4) do_fill_typed<float>(c, s); else do_fill_typed<double>(c, s);
             break;
+        case CMD_AOS_IN: do_aos_in(c, s); break;
+        case CMD_DOWNLOAD_TO: do_download_to(c, s); break;
         case CMD_TEARDOWN: do_teardown(c, s); break;
         default: break;
         }
@@ -938,12 +1016,13 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (!cfg || cfg->struct_size != sizeof(bs_gpu_config)) return BS_GPU_ERR_INVALID;
     if (cfg->fp_bytes != 4 && cfg->fp_bytes != 8) return BS_GPU_ERR_INVALID;
     if (cfg->num_gpus < 1) return BS_GPU_ERR_INVALID;
-    if (cfg->math != BS_MATH_DEFAULT && cfg->math != BS_MATH_IEEE && cfg->math != BS_MATH_FAST) return BS_GPU_ERR_INVALID;
+    if (cfg->math != BS_MATH_DEFAULT && cfg->math != BS_MATH_IEEE && cfg->math != BS_MATH_FAST && cfg->math != BS_MATH_REFERENCE)
+        return BS_GPU_ERR_INVALID;
     if (cfg->unroll != 0 && cfg->unroll != 1 && cfg->unroll != 2 && cfg->unroll != 4) return BS_GPU_ERR_INVALID;
     if (cfg->threads_per_block != 0 && (cfg->threads_per_block < 32 || cfg->threads_per_block > 256 || cfg->threads_per_block % 32))
         return BS_GPU_ERR_INVALID;
     if (cfg->blocks_per_sm < 0 || cfg->blocks_per_sm > 32) return BS_GPU_ERR_INVALID;
-    if (cfg->variant < 0 || cfg->variant > 7) return BS_GPU_ERR_INVALID;
+    if (cfg->variant < 0 || cfg->variant > 15) return BS_GPU_ERR_INVALID;
     if ((cfg->variant & VARIANT_PIPE) && cfg->unroll == 4) return BS_GPU_ERR_INVALID;  // would spill: not built for use
     if (cfg->num_options > 2147483647ull) return BS_GPU_ERR_INVALID;  // the reference's `int numOptions`
 
@@ -1179,6 +1258,46 @@ int bs_gpu_price(bs_gpu_ctx *c, int num_runs, int err_chk, unsigned long long *n
         c->device_valid = true;
     }
     if (num_errors) *num_errors = total;
+    return BS_GPU_OK;
+}
+
+/* The CAF Map's entry (blackscholes.c:482-570): the message is a vector of 24-byte DataCont records. */
+int bs_gpu_price_aos(bs_gpu_ctx *c, const void *records, size_t num_records, float *out_prices, int num_runs)
+{
+    if (!c || num_runs < 0 || (num_records && (!records || !out_prices))) return BS_GPU_ERR_INVALID;
+    {
+        const int ready = finish_setup(c);
+        if (ready != BS_GPU_OK) return ready;
+    }
+    if (c->fp_bytes != 4) return fail(c, BS_GPU_ERR_STATE, "bs_gpu_price_aos: DataCont holds floats; the context must be created with fp_bytes = 4");
+    if (num_records != c->n) return fail(c, BS_GPU_ERR_INVALID, "bs_gpu_price_aos: num_records differs from the context's num_options");
+    const double t0 = now_ms();
+    c->arg_aos = records;
+    c->arg_out = out_prices;
+    int st = broadcast(c, CMD_AOS_IN);
+    if (st != BS_GPU_OK) return st;
+    c->device_valid = true;
+    c->inputs_dirty = false;  // the device now holds the message's options, not the staging buffers' (bs_gpu_mark_dirty to go back)
+    double h2d = 0;
+    for (auto &s : c->shards) h2d = std::max<double>(h2d, s.h2d_ms);
+    c->arg_num_runs = num_runs;
+    c->arg_err_chk = 0;
+    st = broadcast(c, CMD_RUN);
+    if (st != BS_GPU_OK) return st;
+    st = broadcast(c, CMD_DOWNLOAD_TO);
+    if (st != BS_GPU_OK) return st;
+    c->timing.wall_ms = now_ms() - t0;
+    c->timing.h2d_ms = h2d;
+    c->timing.roi_ms = c->timing.d2h_ms = c->timing.pipeline_ms = 0;
+    unsigned long long launches = 0;
+    for (auto &s : c->shards) {
+        c->timing.roi_ms = std::max<double>(c->timing.roi_ms, s.roi_ms);
+        c->timing.d2h_ms = std::max<double>(c->timing.d2h_ms, s.d2h_ms);
+        if (s.count) launches += (unsigned long long)num_runs;
+    }
+    c->timing.kernel_launches = launches;
+    c->timing.h2d_bytes = (unsigned long long)c->n * 24ull;
+    c->timing.d2h_bytes = (unsigned long long)c->n * 4ull;
     return BS_GPU_OK;
 }
 

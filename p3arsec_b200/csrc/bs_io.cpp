@@ -328,9 +328,12 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
     if (f->size >= sizeof(SoaHeader) && memcmp(f->data, SOA_MAGIC, 8) == 0) {
         SoaHeader h;
         memcpy(&h, f->data, sizeof(h));
-        const uint64_t need = SOA_ALIGN + h.stream_stride * SOA_STREAMS;
-        if (h.version != 1 || (h.fp_bytes != 4 && h.fp_bytes != 8) || h.num_options > 2147483647ull ||
-            h.stream_stride < h.num_options * h.fp_bytes || f->size < need) {
+        // Validated by division: a crafted stream_stride must not be able to wrap the size computation.  The
+        // stride has to cover the widest stream (fptype, and the int32 otype stream).
+        const uint64_t widest = h.fp_bytes == 8 ? 8 : 4;
+        const bool stride_ok = f->size >= SOA_ALIGN && h.stream_stride <= (f->size - SOA_ALIGN) / SOA_STREAMS;
+        if (h.version != 1 || (h.fp_bytes != 4 && h.fp_bytes != 8) || h.num_options > 2147483647ull || !stride_ok ||
+            h.stream_stride < h.num_options * widest) {
             bs_io_close(f);
             return BS_IO_ERR_READ;
         }

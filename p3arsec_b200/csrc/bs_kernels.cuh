@@ -35,7 +35,7 @@
 
 namespace bsk {
 
-enum { MATH_PROBE = 0, MATH_IEEE = 1, MATH_FAST = 2 };  // MATH_PROBE: no pricing, traffic only (diagnostic)
+enum { MATH_PROBE = 0, MATH_IEEE = 1, MATH_FAST = 2, MATH_REFERENCE = 3 };  // MATH_PROBE: no pricing, traffic only (diagnostic)
 
 // ---------------------------------------------------------------------------------------------
 // 128-bit streaming accessors
@@ -182,9 +182,70 @@ __device__ __forceinline__ float price_ieee(float s, float k, float r, float v, 
     return otype == 0 ? call : put;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32, BS_MATH_REFERENCE: the reference's fp32 build AS COMPILED -- its constants are double literals, so every
+// expression that touches one is evaluated in double and rounded back to float on assignment (blackscholes.c:154,
+// 156-158,164-170,175,180,232,252-253; verified by disassembly), while literal-free expressions stay in
+// float.  Every operation below is individually rounded (no FMA contraction, like the x86-64 build); expf/logf are
+// evaluated in fp64 and rounded once to fp32, which is what glibc's expf/logf deliver except for arguments whose true
+// result lies within ~0.002 ulp of a rounding boundary (their error bound is 0.502 ulp).  This is the validation
+// mode: its distance to the reference CPU output separates "rounding of the reference" from "kernel defect".
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ref_expf(float x) { return __double2float_rn(exp((double)x)); }
+__device__ __forceinline__ float ref_logf(float x) { return __double2float_rn(log((double)x)); }
+__device__ __forceinline__ float ref_mul_lit(float a, double lit) { return __double2float_rn(__dmul_rn((double)a, lit)); }
+
+__device__ __noinline__ float cndf_reference(float x)
+{
+    const bool neg = x < 0.0f;                                             // :144-148
+    if (neg) x = -x;
+    const float ax = x;
+    float npx = ref_expf(__fmul_rn(__fmul_rn(-0.5f, x), x));               // :152  float literal: stays in fptype
+    npx = ref_mul_lit(npx, 0.39894228040143270286);                        // :154
+    float k1 = ref_mul_lit(ax, 0.2316419);                                 // :156
+    k1 = __double2float_rn(__dadd_rn(1.0, (double)k1));                    // :157
+    k1 = __double2float_rn(__ddiv_rn(1.0, (double)k1));                    // :158
+    const float k2 = __fmul_rn(k1, k1);                                    // :159-162
+    const float k3 = __fmul_rn(k2, k1);
+    const float k4 = __fmul_rn(k3, k1);
+    const float k5 = __fmul_rn(k4, k1);
+    float lead = ref_mul_lit(k1, 0.319381530);                             // :164
+    float acc = ref_mul_lit(k2, -0.356563782);                             // :165
+    acc = __fadd_rn(acc, ref_mul_lit(k3, 1.781477937));                    // :166-167
+    acc = __fadd_rn(acc, ref_mul_lit(k4, -1.821255978));                   // :168-169
+    acc = __fadd_rn(acc, ref_mul_lit(k5, 1.330274429));                    // :170-171
+    lead = __fadd_rn(acc, lead);                                           // :173
+    float out = __fmul_rn(lead, npx);                                      // :174
+    out = __double2float_rn(__dsub_rn(1.0, (double)out));                  // :175
+    if (neg) out = __double2float_rn(__dsub_rn(1.0, (double)out));         // :179-181
+    return out;
+}
+
+__device__ __forceinline__ float price_reference(float s, float k, float r, float v, float t, int otype)
+{
+    const float sq = __fsqrt_rn(t);                                        // :224
+    const float lg = ref_logf(__fdiv_rn(s, k));                            // :226
+    float pw = __fmul_rn(v, v);                                            // :231
+    pw = ref_mul_lit(pw, 0.5);                                             // :232
+    float d1 = __fadd_rn(r, pw);                                           // :234
+    d1 = __fmul_rn(d1, t);                                                 // :235
+    d1 = __fadd_rn(d1, lg);                                                // :236
+    const float den = __fmul_rn(v, sq);                                    // :238
+    d1 = __fdiv_rn(d1, den);                                               // :239
+    const float d2 = __fsub_rn(d1, den);                                   // :240
+    const float n1 = cndf_reference(d1);                                   // :245
+    const float n2 = cndf_reference(d2);                                   // :246
+    const float fv = __fmul_rn(k, ref_expf(__fmul_rn(-r, t)));             // :248
+    if (otype == 0) return __fsub_rn(__fmul_rn(s, n1), __fmul_rn(fv, n2)); // :250
+    const float m1 = __double2float_rn(__dsub_rn(1.0, (double)n1));        // :252
+    const float m2 = __double2float_rn(__dsub_rn(1.0, (double)n2));        // :253
+    return __fsub_rn(__fmul_rn(fv, m2), __fmul_rn(s, m1));                 // :254
+}
+
 template <int MATH>
 __device__ __forceinline__ float price_f32(float s, float k, float r, float v, float t, int otype)
 {
+    if (MATH == MATH_REFERENCE) return price_reference(s, k, r, v, t, otype);
     // MATH_PROBE is a measurement aid, not a pricing mode: same seven streams, same access pattern, five adds.
     // Its bandwidth is the ceiling of THIS traffic pattern (6 read streams : 1 write stream) on the device.
     if (MATH == MATH_PROBE) return s + k + r + v + t + (float)otype;
@@ -252,7 +313,7 @@ __device__ __forceinline__ double price_f64_any(double s, double k, double r, do
         if (__builtin_expect(ok, 1)) return p;
         return price_f64_cold(s, k, r, v, t, otype);
     }
-    return price_f64(s, k, r, v, t, otype);
+    return price_f64(s, k, r, v, t, otype);  // MATH_IEEE and MATH_REFERENCE: with fptype=double nothing is promoted
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -597,6 +658,39 @@ __global__ void __launch_bounds__(256) bs_fill_synthetic(TableDev<FP> tab, unsig
         otime[i] = tab.otime[row];
         otype[i] = tab.otype[row];
         if (refval) refval[i] = tab.refval[row];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AoS -> SoA gather for the CAF Map's message layout (blackscholes.c:482-489): records of
+//     struct DataCont { int otype; float sptprice, strike, rate, volatility, otime; }   (24 bytes)
+// A CTA moves AOS_TILE consecutive records: coalesced 128-bit loads of the tile into shared memory (the tile is
+// 6 KB = 384 x 16 B), then thread t reads the six words of record t (stride 6 words: 2-way bank conflict at worst)
+// and writes one element of each SoA stream, so every global access of the kernel is coalesced.  `aos` must be
+// 16-byte aligned and readable up to a whole tile past the last record (the arena is padded accordingly).
+// ---------------------------------------------------------------------------------------------
+enum { AOS_TILE = 256, AOS_WORDS = 6 };
+
+__global__ void __launch_bounds__(AOS_TILE) bs_aos_to_soa(const uint4 *aos, size_t n, float *spt, float *strike, float *rate,
+                                                          float *vol, float *otime, int *otype)
+{
+    __shared__ __align__(16) uint32_t tile[AOS_TILE * AOS_WORDS];
+    const size_t tiles = (n + AOS_TILE - 1) / AOS_TILE;
+    for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint4 *src = aos + t * (AOS_TILE * AOS_WORDS / 4);
+        for (int q = threadIdx.x; q < AOS_TILE * AOS_WORDS / 4; q += AOS_TILE) reinterpret_cast<uint4 *>(tile)[q] = src[q];
+        __syncthreads();
+        const size_t i = t * AOS_TILE + threadIdx.x;
+        if (i < n) {
+            const uint32_t *rec = tile + threadIdx.x * AOS_WORDS;
+            otype[i] = (int)rec[0];
+            spt[i] = __uint_as_float(rec[1]);
+            strike[i] = __uint_as_float(rec[2]);
+            rate[i] = __uint_as_float(rec[3]);
+            vol[i] = __uint_as_float(rec[4]);
+            otime[i] = __uint_as_float(rec[5]);
+        }
+        __syncthreads();
     }
 }
 

@@ -186,11 +186,15 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double x2 = ((d2 < 0.0) != put) ? w2 : 1.0 - w2;
     const double c = fma(s, x1, -(fv * x2));
     // Domain of the blocks above: t, k*v and s/k positive normal numbers well inside the exponent range
-    // (biased exponent in [0x100, 0x6ff], i.e. 2^-767 .. 2^768).  Three integer range checks on the high words;
-    // everything else (t = 0, v = 0, s <= 0, NaN, inf, denormals) is left to the IEEE-order path.
+    // (biased exponent in [0x100, 0x6ff], i.e. 2^-767 .. 2^768); the product a1*a2 = (1 + c|d1|)(1 + c|d2|) fed to the
+    // shared reciprocal finite (it overflows for v below ~1e-154, where |d| ~ 1/v: rcp(inf) = 0 and 0 * inf = NaN
+    // where the reference still returns the intrinsic value); and |r t| < 2^9, so exp_f64's exponent arithmetic cannot
+    // wrap (the reference returns inf / NaN there, exp_f64 a finite number).  Integer range checks on the high
+    // words; everything else (t = 0, v = 0, s <= 0, NaN, inf, denormals, overflow) is left to the IEEE-order path.
     const uint32_t LO = 0x10000000u, SPAN = 0x60000000u;
+    const uint32_t hi_a = (uint32_t)(to_bits(a1 * a2) >> 32), hi_rt = (uint32_t)(to_bits(r * t) >> 32) & 0x7fffffffu;
     *ok = ((uint32_t)(to_bits(t) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(k * v) >> 32) - LO < SPAN) &&
-          ((uint32_t)(to_bits(s * inv_k) >> 32) - LO < SPAN);
+          ((uint32_t)(to_bits(s * inv_k) >> 32) - LO < SPAN) && (hi_a < 0x6ff00000u) && (hi_rt < 0x40800000u);
     return put ? -c : c;
 }
 

@@ -231,11 +231,52 @@ int sw_gpu_set_geometry(sw_gpu_ctx *c, int ctas_per_sm, int trials_per_thread)
     return SW_GPU_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Every device's streams drained: nothing launched by a failed sw_gpu_price() may still read the pinned parameter
+// records or write the pinned results when the call returns (a later call, or sw_gpu_fini's cudaFreeHost, would race).
+void quiesce(sw_gpu_ctx *c)
+{
+    for (auto &d : c->devs) {
+        if (cudaSetDevice(d.device) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        for (int k = 0; k < AUX_STREAMS; ++k)
+            if (d.aux[k]) cudaStreamSynchronize(d.aux[k]);
+        cudaGetLastError();
+    }
+}
+
+int price_impl(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions, const double *pdYield,
+               const double *ppdFactors, long swaption_seed, long lTrials, int BLOCKSIZE, unsigned flags, double *mean,
+               double *std_error);
+
+}  // namespace
+
+extern "C" {
+
 int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions, const double *pdYield,
                  const double *ppdFactors, long swaption_seed, long lTrials, int BLOCKSIZE, unsigned flags, double *mean,
                  double *std_error)
 {
     if (!c) return SW_GPU_ERR_INVALID;
+    const int st = price_impl(c, nSwaptions, swaptions, pdYield, ppdFactors, swaption_seed, lTrials, BLOCKSIZE, flags, mean, std_error);
+    if (st != SW_GPU_OK) {  // one cleanup path for every failure, wherever in the per-device loop it happened
+        quiesce(c);
+        memset(&c->timing, 0, sizeof(c->timing));
+    }
+    return st;
+}
+
+}  // extern "C"
+
+namespace {
+
+int price_impl(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions, const double *pdYield,
+               const double *ppdFactors, long swaption_seed, long lTrials, int BLOCKSIZE, unsigned flags, double *mean,
+               double *std_error)
+{
     if (nSwaptions < 0 || nSwaptions > c->max_swaptions || (nSwaptions > 0 && (!swaptions || !pdYield || !ppdFactors || !mean || !std_error)))
         return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: bad arguments (nSwaptions = %d, capacity %d)", nSwaptions, c->max_swaptions);
     if (BLOCKSIZE < 1 || lTrials < 0) return fail(c, SW_GPU_ERR_INVALID, "sw_gpu_price: BLOCKSIZE %d, lTrials %ld", BLOCKSIZE, lTrials);
@@ -267,10 +308,6 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
         for (int i = d.first; i < d.first + d.count; ++i) {
             if (!swk::prepare(c->h_params[i], swaptions[i], iN, nF, pdYield + (size_t)i * iN, ppdFactors + (size_t)i * nF * (iN - 1),
                          swaption_seed + i, lTrials, BLOCKSIZE)) {
-                for (int h = 0; h < g; ++h) {  // let what was launched finish before reporting
-                    if (cudaSetDevice(c->devs[h].device) == cudaSuccess) cudaStreamSynchronize(c->devs[h].stream);
-                }
-                memset(&c->timing, 0, sizeof(c->timing));
                 return fail(c, SW_GPU_ERR_INVALID, "swaption %d: dYears/dMaturity/dTenor/dPaymentInterval put a time index outside the %d-point HJM path", i, iN);
             }
         }
@@ -378,6 +415,10 @@ int sw_gpu_price(sw_gpu_ctx *c, int nSwaptions, const sw_gpu_swaption *swaptions
     c->timing.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     return SW_GPU_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int sw_gpu_get_timing(sw_gpu_ctx *c, sw_gpu_timing *out)
 {

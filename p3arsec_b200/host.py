@@ -15,23 +15,28 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbs_gpu.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enum bs_gpu_buffer
 BUF_SPTPRICE, BUF_STRIKE, BUF_RATE, BUF_VOLATILITY, BUF_OTIME, BUF_OTYPE, BUF_PRICES, BUF_DGREFVAL = range(8)
 BUF_NAMES = ("sptprice", "strike", "rate", "volatility", "otime", "otype", "prices", "dgrefval")
 # enum bs_gpu_math
-MATH_DEFAULT, MATH_IEEE, MATH_FAST = 0, 1, 2
+MATH_DEFAULT, MATH_IEEE, MATH_FAST, MATH_REFERENCE = 0, 1, 2, 3
 # flags
 FLAG_NO_HOST_STAGING, FLAG_WITH_DGREFVAL, FLAG_NO_GRAPH, FLAG_ASYNC_DISCOVERY, FLAG_PDL, FLAG_NO_SUBSHARDS = 1, 2, 4, 8, 16, 32
 
 NUM_RUNS = 100  # blackscholes.c:87
 
+# struct DataCont of the CAF Map (blackscholes.c:482-489): the record layout bs_gpu_price_aos() takes
+DATACONT_DTYPE = np.dtype([("otype", np.int32), ("sptprice", np.float32), ("strike", np.float32), ("rate", np.float32),
+                           ("volatility", np.float32), ("otime", np.float32)])
+assert DATACONT_DTYPE.itemsize == 24
+
 # every symbol include/bs_gpu.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = (
     "bs_gpu_abi_version", "bs_gpu_status_string", "bs_gpu_device_count", "bs_gpu_init", "bs_gpu_init_ex",
     "bs_gpu_host_buffer", "bs_gpu_mark_dirty", "bs_gpu_price", "bs_gpu_upload", "bs_gpu_run", "bs_gpu_download",
-    "bs_gpu_fill_synthetic", "bs_gpu_read_device", "bs_gpu_errors", "bs_gpu_num_shards", "bs_gpu_shard",
+    "bs_gpu_price_aos", "bs_gpu_fill_synthetic", "bs_gpu_read_device", "bs_gpu_errors", "bs_gpu_num_shards", "bs_gpu_shard",
     "bs_gpu_get_timing", "bs_gpu_get_launch", "bs_gpu_last_error", "bs_gpu_fini",
 )
 
@@ -97,6 +102,7 @@ def load_library(path=None):
     L.bs_gpu_upload.restype, L.bs_gpu_upload.argtypes = ci, [vp]
     L.bs_gpu_run.restype, L.bs_gpu_run.argtypes = ci, [vp, ci, ci, pull]
     L.bs_gpu_download.restype, L.bs_gpu_download.argtypes = ci, [vp]
+    L.bs_gpu_price_aos.restype, L.bs_gpu_price_aos.argtypes = ci, [vp, vp, cs, vp, ci]
     L.bs_gpu_fill_synthetic.restype, L.bs_gpu_fill_synthetic.argtypes = ci, [vp, ctypes.c_ulonglong]
     L.bs_gpu_read_device.restype, L.bs_gpu_read_device.argtypes = ci, [vp, ci, cs, cs, vp]
     L.bs_gpu_errors.restype, L.bs_gpu_errors.argtypes = ctypes.c_longlong, [vp, ctypes.POINTER(ctypes.c_longlong), cs]
@@ -217,6 +223,14 @@ class BlackScholesGPU:
         self._check(self._L.bs_gpu_price(self._ctx, num_runs, 1 if err_chk else 0, ctypes.byref(errs)), "bs_gpu_price")
         return errs.value
 
+    def price_aos(self, records, num_runs=NUM_RUNS):
+        """bs_gpu_price_aos: the CAF Map's message (DATACONT_DTYPE records, blackscholes.c:482-489) -> prices."""
+        rec = np.ascontiguousarray(records, dtype=DATACONT_DTYPE)
+        out = np.empty(rec.shape[0], dtype=np.float32)
+        self._check(self._L.bs_gpu_price_aos(self._ctx, rec.ctypes.data_as(ctypes.c_void_p), rec.shape[0],
+                                             out.ctypes.data_as(ctypes.c_void_p), num_runs), "bs_gpu_price_aos")
+        return out
+
     def upload(self):
         self._check(self._L.bs_gpu_upload(self._ctx), "bs_gpu_upload")
 
@@ -262,7 +276,7 @@ class BlackScholesGPU:
     def launch(self):
         m, t, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._check(self._L.bs_gpu_get_launch(self._ctx, ctypes.byref(m), ctypes.byref(t), ctypes.byref(b)), "bs_gpu_get_launch")
-        return {"math": {1: "ieee", 2: "fast"}.get(m.value, str(m.value)), "threads_per_block": t.value, "blocks": b.value}
+        return {"math": {1: "ieee", 2: "fast", 3: "reference"}.get(m.value, str(m.value)), "threads_per_block": t.value, "blocks": b.value}
 
 
 def bytes_per_option(fp_bytes, err_chk=False):

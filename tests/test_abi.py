@@ -67,6 +67,7 @@ def test_init_rejects_bad_arguments_before_touching_a_device(kw):
 def test_null_context_calls_are_safe():
     L = host.load_library()
     assert L.bs_gpu_price(None, 1, 0, None) == -1
+    assert L.bs_gpu_price_aos(None, None, 0, None, 1) == -1
     assert L.bs_gpu_upload(None) == -1 and L.bs_gpu_run(None, 1, 0, None) == -1 and L.bs_gpu_download(None) == -1
     assert L.bs_gpu_host_buffer(None, 0) is None
     assert L.bs_gpu_num_shards(None) == -1
@@ -143,4 +144,4 @@ def test_headers_are_plain_c_and_link(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
                     "-L", lib_dir, "-lbs_gpu", "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.split() == ["1", "-1", "no", "usable", "CUDA", "device", "8"]
+    assert out.returncode == 0 and out.stdout.split() == [str(host.ABI_VERSION), "-1", "no", "usable", "CUDA", "device", "8"]

@@ -224,7 +224,9 @@ def test_native_size_properties():
 def test_shards_over_devices():
     n_dev = sw.device_count()
     if n_dev < 2:
-        pytest.skip("needs >= 2 GPUs")
+        msg = "SKIPPED (LOUD): test_shards_over_devices needs >= 2 GPUs in ONE process; this box shows %d" % n_dev
+        print("\n" + "!" * 100 + "\n" + msg + "\n" + "!" * 100)
+        pytest.skip(msg)
     seed, p, y, f = sw.make_portfolio(13)
     one = gpu_price(p, y, f, seed, 8192, 0)
     for g in range(2, min(n_dev, 8) + 1):
