@@ -73,7 +73,7 @@ typedef enum bs_gpu_buffer {
  * Accuracy contract (measured worst cases: DESIGN.md section 4 and profiles/r02_fp32_adversarial.json):
  *   fp32, operands in the PARSEC inputgen range (spot, strike <= 128; 0.05 <= v <= 0.65; 0.05 <= t <= 1):
  *         every mode: |price - reference CPU price| <= 1e-4, the reference's own ERR_CHK threshold
- *         (blackscholes.c:335).  BS_MATH_REFERENCE is typically bit-identical (worst measured distance in DESIGN.md).
+ *         (blackscholes.c:335).  BS_MATH_REFERENCE reproduces the reference CPU output bit for bit.
  *   fp32, larger operands: BS_MATH_REFERENCE keeps the flat 1e-4 bound; BS_MATH_FAST / BS_MATH_IEEE keep the same
  *         number of ulps, i.e. the bound scales as 1e-4 * max(1, max(spot, strike) / 128): a price near 1000 is
  *         itself quantised to 6e-5 in fp32 and the reference's own fp32 build is 1.7e-4 from its fp64 build there.
@@ -88,8 +88,9 @@ typedef enum bs_gpu_math {
                              path taken for operands outside its range (t = 0, v = 0, denormals, overflow)       */
     BS_MATH_REFERENCE = 3 /* fp32: the reference's fp32 build as compiled -- same operation order AND its double
                              promotions (blackscholes.c:154-158,164-175,232,252-253), every operation individually
-                             rounded, expf/logf correctly rounded from fp64.  The validation mode: several times
-                             slower than FAST.  fp64: identical to BS_MATH_IEEE (nothing is promoted)             */
+                             rounded, expf/logf = glibc 2.39's algorithms (csrc/bs_libm_f32.h, pinned against the
+                             host libm over all 2^32 floats): the reference CPU prices, bit for bit.  The validation
+                             mode: several times slower than FAST.  fp64: identical to BS_MATH_IEEE               */
 } bs_gpu_math;
 
 /* bs_gpu_config.flags */

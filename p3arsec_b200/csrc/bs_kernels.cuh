@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bs_libm_f32.h"
 #include "bs_math_f64.h"
 
 namespace bsk {
@@ -186,13 +187,13 @@ __device__ __forceinline__ float price_ieee(float s, float k, float r, float v, 
 // fp32, BS_MATH_REFERENCE: the reference's fp32 build AS COMPILED -- its constants are double literals, so every
 // expression that touches one is evaluated in double and rounded back to float on assignment (blackscholes.c:154,
 // 156-158,164-170,175,180,232,252-253; verified by disassembly), while literal-free expressions stay in
-// float.  Every operation below is individually rounded (no FMA contraction, like the x86-64 build); expf/logf are
-// evaluated in fp64 and rounded once to fp32, which is what glibc's expf/logf deliver except for arguments whose true
-// result lies within ~0.002 ulp of a rounding boundary (their error bound is 0.502 ulp).  This is the validation
-// mode: its distance to the reference CPU output separates "rounding of the reference" from "kernel defect".
+// float.  Every operation below is individually rounded (no FMA contraction, like the x86-64 build), and expf/logf
+// are glibc 2.39's own algorithms restated in bs_libm_f32.h (bit-identical to the host libm over all 2^32 floats).
+// The result is the reference CPU output BIT FOR BIT; this is the validation mode: it separates "rounding of the
+// reference" from "kernel defect" for the fast modes, at several times their cost.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ref_expf(float x) { return __double2float_rn(exp((double)x)); }
-__device__ __forceinline__ float ref_logf(float x) { return __double2float_rn(log((double)x)); }
+__device__ __forceinline__ float ref_expf(float x) { return bsl::expf_glibc(x); }
+__device__ __forceinline__ float ref_logf(float x) { return bsl::logf_glibc(x); }
 __device__ __forceinline__ float ref_mul_lit(float a, double lit) { return __double2float_rn(__dmul_rn((double)a, lit)); }
 
 __device__ __noinline__ float cndf_reference(float x)

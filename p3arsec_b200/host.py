@@ -252,6 +252,13 @@ class BlackScholesGPU:
         self._check(self._L.bs_gpu_read_device(self._ctx, which, first, count, out.ctypes.data_as(ctypes.c_void_p)), "bs_gpu_read_device")
         return out
 
+    def read_device_into(self, which, first, dst):
+        """bs_gpu_read_device straight into `dst` (a contiguous numpy array, e.g. a slice of a pinned host stream)."""
+        if isinstance(which, str):
+            which = BUF_NAMES.index(which)
+        assert dst.flags["C_CONTIGUOUS"] and dst.dtype == (np.int32 if which == BUF_OTYPE else self.dtype)
+        self._check(self._L.bs_gpu_read_device(self._ctx, which, first, dst.shape[0], dst.ctypes.data_as(ctypes.c_void_p)), "bs_gpu_read_device")
+
     def errors(self, cap=65536):
         idx = np.empty(cap, dtype=np.int64)
         n = self._L.bs_gpu_errors(self._ctx, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), cap)

@@ -339,8 +339,7 @@ def test_fp32_reference_mode_against_golden_flat_bound(name):
     worst = assert_parity(got, ref, 4, "%s/reference" % name)
     exact = float(np.mean(got.astype(np.float64) == ref))
     print("fp32 %-9s reference-mode max|delta| = %.3e, bit-identical on %.2f%% of rows" % (name, worst, 100 * exact))
-    assert worst <= 2e-5   # far inside the bound: only last-ulp differences of expf/logf remain
-    assert exact >= 0.9
+    assert worst == 0.0 and exact == 1.0   # the reference CPU output, bit for bit (expf/logf are glibc's own algorithms)
 
 
 def test_fp32_reference_mode_native_10m():
@@ -351,7 +350,7 @@ def test_fp32_reference_mode_native_10m():
     worst = assert_parity(got, ref, 4, "10M/reference")
     exact = float(np.mean(got == ref))
     print("fp32 reference mode, 10M random inputgen-range options: max|delta| vs oracle = %.3e, bit-identical %.3f%%" % (worst, 100 * exact))
-    assert worst <= 2e-5 and exact >= 0.95
+    assert worst == 0.0 and exact == 1.0
 
 
 def test_fp32_reference_mode_err_chk_and_sizes():

@@ -1,0 +1,132 @@
+#!/usr/bin/env python3
+"""Adversarial search for the largest distance between the CUDA fp32 prices and the reference CPU output.
+
+VERDICT r1 "Next" 3(b): the 1e-4 bound of north_star was so far only checked on random draws.  This tool prices, on the
+GPU through the C ABI and with the oracle (bit-identical to the compiled reference, tests/test_oracle.py) on the host,
+
+  A. the PARSEC inputgen domain, structured: every (v, t) on the 2-decimal grid v in 0.05..0.65, t in 0.05..1.00, every
+     rate of the table, spots at the ends and in the middle of 20..120, and for each a sweep of strikes that walks d1
+     over [-6, 6] (strike = s exp(-(d1 v sqrt t - (r + v^2/2) t)), rounded to 2 decimals like the input format, clipped
+     to the generator's strike/spot range 0.7..1.3), calls and puts;
+  B. the same sweep WITHOUT the strike/spot clip (any moneyness, operands still <= 128): deep in/out of the money;
+  C. >= 200M random options of the inputgen distribution (fresh seeds);
+
+for BS_MATH_FAST, BS_MATH_IEEE and BS_MATH_REFERENCE, and records the worst |delta| per mode and domain together with
+the option that produced it.  Prints one JSON object (and writes it to --out).
+
+    python tools/fp32_adversarial.py [--random-millions 200] [--out gpurun_out/r02_fp32_adversarial.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracle_lib: this tool is a checker, not product code
+
+RATES = np.array([0.0250, 0.0275, 0.0500, 0.0750, 0.1000])
+SPOTS = np.array([20.00, 20.01, 33.33, 50.00, 64.00, 99.99, 100.00, 120.00])
+D1_GRID = np.linspace(-6.0, 6.0, 49)
+
+
+def sweep(clip):
+    """Structured options: (v, t, r, s) grid x d1 sweep.  Yields chunks of float32 SoA inputs."""
+    v = np.round(np.arange(5, 66) * 0.01, 2)
+    t = np.round(np.arange(5, 101) * 0.01, 2)
+    for r in RATES:
+        V, T, S, D = np.meshgrid(v, t, SPOTS, D1_GRID, indexing="ij")
+        V, T, S, D = (a.ravel() for a in (V, T, S, D))
+        sq = V * np.sqrt(T)
+        K = S * np.exp(-(D * sq - (r + 0.5 * V * V) * T))
+        if clip:
+            K = np.clip(K, 0.7 * S, 1.3 * S)
+        else:
+            K = np.clip(K, 0.01, 128.0)
+        K = np.round(K, 2)
+        R = np.full_like(S, r)
+        for o in (0, 1):
+            yield tuple(a.astype(np.float32) for a in (S, K, R, V, T)) + (np.full(S.shape, o, np.int32),)
+
+
+def random_chunks(millions, chunk=10_000_000):
+    from gpu_util import inputgen_like
+    done = 0
+    seed = 20261017
+    while done < millions * 1_000_000:
+        yield inputgen_like(chunk, seed=seed)
+        seed += 1
+        done += chunk
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--random-millions", type=int, default=200)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    import oracle_lib
+    from p3arsec_b200 import host
+
+    modes = (("fast", host.MATH_FAST), ("ieee", host.MATH_IEEE), ("reference", host.MATH_REFERENCE))
+    report = {"tool": "tools/fp32_adversarial.py", "bound": 1e-4, "domains": {}}
+    t0 = time.time()
+    for dom, gen, desc in (
+            ("A_inputgen_structured", lambda: sweep(True), "v,t on the 2-decimal grid x 5 rates x 8 spots x d1 in [-6,6] (49 strikes), strike/spot clipped to 0.7..1.3, calls+puts"),
+            ("B_any_moneyness", lambda: sweep(False), "same sweep, strike unclipped (0.01..128): deep in/out of the money"),
+            ("C_inputgen_random", lambda: random_chunks(a.random_millions), "random options of the inputgen distribution, fresh seeds")):
+        worst = {m: {"max_abs_delta": 0.0, "option": None, "bit_identical": 0} for m, _ in modes}
+        count = 0
+        ref_vs_f64 = 0.0
+        ctxs = {}
+        for inputs in gen():
+            n = len(inputs[0])
+            ref = oracle_lib.price_map(*inputs, fp_bytes=4).astype(np.float64)
+            ref64 = oracle_lib.price_map(*[x.astype(np.float64) for x in inputs[:5]], inputs[5], fp_bytes=8)
+            fin = np.isfinite(ref)
+            ref_vs_f64 = max(ref_vs_f64, float(np.abs(ref - ref64)[fin].max()))
+            for m, code in modes:
+                key = (m, n)
+                if key not in ctxs:
+                    for k in [k for k in ctxs if k[0] == m]:
+                        ctxs.pop(k).close()
+                    ctxs[key] = host.BlackScholesGPU(n, math=code, with_dgrefval=False)
+                bs = ctxs[key]
+                bs.set_inputs(*inputs)
+                bs.price(1)
+                got = bs.prices.astype(np.float64)
+                if not (np.isfinite(got) == fin).all():
+                    raise SystemExit("%s/%s: finiteness differs from the reference" % (dom, m))
+                d = np.abs(got - ref)
+                d[~fin] = 0
+                i = int(d.argmax())
+                w = worst[m]
+                w["bit_identical"] += int((got == ref).sum())
+                if d[i] > w["max_abs_delta"]:
+                    w["max_abs_delta"] = float(d[i])
+                    w["option"] = {"s": float(inputs[0][i]), "strike": float(inputs[1][i]), "r": float(inputs[2][i]), "v": float(inputs[3][i]),
+                                   "t": float(inputs[4][i]), "otype": int(inputs[5][i]), "gpu": float(got[i]), "reference": float(ref[i])}
+            count += n
+        for c in ctxs.values():
+            c.close()
+        for m, _ in modes:
+            worst[m]["bit_identical_frac"] = worst[m].pop("bit_identical") / max(count, 1)
+            worst[m]["margin_to_bound"] = 1.0 - worst[m]["max_abs_delta"] / 1e-4
+        report["domains"][dom] = {"what": desc, "options": count, "reference_fp32_vs_its_fp64_build_max_abs": ref_vs_f64, "modes": worst}
+        print("[%6.1f s] %-22s %11d options: " % (time.time() - t0, dom, count) +
+              ", ".join("%s %.3e" % (m, worst[m]["max_abs_delta"]) for m, _ in modes), file=sys.stderr, flush=True)
+    report["total_options"] = sum(d["options"] for d in report["domains"].values())
+    report["seconds"] = time.time() - t0
+    line = json.dumps(report)
+    print(line)
+    if a.out:
+        os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+        with open(a.out, "w") as f:
+            f.write(json.dumps(report, indent=1) + "\n")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
