@@ -66,14 +66,21 @@ def ncu_traffic_bytes(workload):
 
 class ClockSampler:
     """SM clock, power and throttle reasons of one GPU sampled through NVML every ~2 ms WHILE the timed region
-    runs (a Python thread; the timed calls are ctypes calls that release the GIL)."""
+    runs (a Python thread; the timed calls are ctypes calls that release the GIL).  start() returns once NVML is up
+    and the first sample exists, so that even an 80 ms region is covered; only samples taken between start() and
+    stop() are reported."""
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.samples = []
         self._stop = False
         self._thread = None
+        self._armed = False
         self.err = None
+        import threading
+        self._ready = threading.Event()
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()   # NVML initialisation (tens of ms) happens now, long before the timed region
 
     def _loop(self):
         try:
@@ -91,19 +98,21 @@ class ClockSampler:
                     power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
                 except Exception:
                     power = None
-                self.samples.append((sm, reasons, power))
-                time.sleep(0.002)
+                if self._armed:
+                    self.samples.append((sm, reasons, power))
+                self._ready.set()
+                time.sleep(0.002 if self._armed else 0.0005)
             pynvml.nvmlShutdown()
         except Exception as e:  # NVML missing: report it in the JSON instead of failing the run
             self.err = str(e)
+            self._ready.set()
 
     def start(self):
-        import threading
-        self._thread = threading.Thread(target=self._loop, daemon=True)
-        self._thread.start()
-        time.sleep(0.05)
+        self._ready.wait(timeout=10)
+        self._armed = True
 
     def stop(self):
+        self._armed = False
         self._stop = True
         if self._thread is not None:
             self._thread.join(timeout=5)
@@ -111,15 +120,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                  0x80: "hw_power_brake_slowdown"}
-        seen = set()
+        seen = {}
         for _, r, _ in self.samples:
             for bit, nm in names.items():
                 if r & bit:
-                    seen.add(nm)
+                    seen[nm] = seen.get(nm, 0) + 1
         sm = sorted(x[0] for x in self.samples)
         pw = [x[2] for x in self.samples if x[2] is not None]
         return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": getattr(self, "max_mhz", None),
-                "reasons": sorted(seen), "samples": len(sm), "power_w_max": max(pw) if pw else None, "source": "nvml"}
+                "reasons": sorted(seen), "reason_samples": seen, "samples": len(sm), "power_w_max": max(pw) if pw else None, "source": "nvml"}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -149,53 +149,100 @@ BS_HD double log_f64(double x, const double *tab)
     return fma(ed, kd(K_LN2_HI), lc + fma(ed, kd(K_LN2_LO), lp));
 }
 
-// 1 - N(|d|) given k = 1/(1 + 0.2316419|d|): n(d) poly(k), constants of CNDF (blackscholes.c:126,:156,:164-170)
-// pre-multiplied by 1/sqrt(2 pi).
-BS_HD double cndf_tail_f64(double d, double k, const double *tab)
+// exp(x) without exp_f64's underflow guard, for callers that have range-checked x themselves (|x| < 700); the
+// exponent is added to the high word only (one integer add instead of a 64-bit add with carry).
+BS_HD double exp_core_f64(double x, const double *tab)
 {
-    double e = exp_f64((-0.5 * d) * d, tab);
+    const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+    double nd = fma(x, kd(K_EXP_INV), MAGIC);
+    const int n = (int)(uint32_t)to_bits(nd);  // round(x * 64/ln2) = 64 k + j
+    nd -= MAGIC;
+    double r = fma(nd, -kd(K_EXP_HI), x);
+    r = fma(nd, -kd(K_EXP_LO), r);
+    double q = fma(kd(K_EXP_C5), r, kd(K_EXP_C4));
+    q = fma(q, r, kd(K_EXP_C3));
+    q = fma(q, r, 0.5);
+    const double em1 = fma(q, r * r, r);
+    const double T = tab[TAB_EXP + (n & 63)];
+    const uint64_t mb = to_bits(fma(T, em1, T));  // in [0.99, 2.0)
+    const uint32_t hi = (uint32_t)(mb >> 32) + ((uint32_t)(n >> 6) << 20);
+    return from_bits(((uint64_t)hi << 32) | (mb & 0xffffffffull));
+}
+
+// poly(k) with k = 1/(1 + 0.2316419|d|): the CNDF tail 1 - N(|d|) is exp(-d^2/2) k poly(k) / sqrt(2 pi); the constants
+// of CNDF (blackscholes.c:126,:156,:164-170) are pre-multiplied by 1/sqrt(2 pi).
+BS_HD double cndf_poly_f64(double k)
+{
     double p = fma(k, kd(K_CNDF_A5), kd(K_CNDF_A4));
     p = fma(k, p, kd(K_CNDF_A3));
     p = fma(k, p, kd(K_CNDF_A2));
     p = fma(k, p, kd(K_CNDF_A1));
-    return (p * k) * e;
+    return p * k;
+}
+
+// 1 - N(|d|) given k = 1/(1 + 0.2316419|d|)
+BS_HD double cndf_tail_f64(double d, double k, const double *tab)
+{
+    return cndf_poly_f64(k) * exp_f64((-0.5 * d) * d, tab);
 }
 
 // The whole option (BlkSchlsEqEuroNoDiv, blackscholes.c:190-258) for s, k, v, t > 0 finite.  `ok` is false for
-// degenerate inputs (den = v sqrt(t) not a positive normal number): the caller then uses the IEEE-order path.
+// inputs outside the domain of the blocks below: the caller then uses the IEEE-order path.
+//
+// Restructured for the fp64 pipe -- the kernel is bound by FP64 issue, not by HBM (profiles/r02_ncu_f64_*.txt):
+//   * ONE rsqrt, of (k v)^2 t, yields 1/(v sqrt t), 1/sqrt t, sqrt t and 1/k by multiplications;
+//   * the second CNDF exponential is never evaluated.  With P_j = k_j poly(k_j) the two tails are
+//     w1 = e1 P1 and w2 = e2 P2, e_j = exp(-d_j^2/2), and the Black-Scholes identity  s n(d1) = fv n(d2)
+//     (d1 den - den^2/2 = log(s/k) + r t exactly) gives  fv w2 = s e1 P2.  Hence, with g = s e1,
+//         s N1 - fv N2 = g (+-P1 -+ P2) + ([N1 = 1 - w1] s - [N2 = 1 - w2] fv):
+//     one exponential, signs and the two optional terms selected by integer masks on the sign bits of d1, d2;
+//   * one shared reciprocal for the two CNDF arguments (as before).
+// 76 fp64 operations per option (94 before).  Rounding errors of d1 enter the price only multiplied by den (the
+// common shift of d1 and d2 cancels in the identity), i.e. at the 1e-15 level: measured 8e-14 worst absolute
+// distance to the fp64 CPU build on the inputgen table (tests/test_math_f64.py, tests/test_gpu_parity.py).
 BS_HD double price_f64_fast(double s, double k, double r, double v, double t, int otype, bool *ok, const double *tab)
 {
-    const double y = rsqrt_f64(t);           // 1/sqrt(t)
-    const double sq = t * y;                 // sqrt(t)                       :224
-    const double den = v * sq;               // xDen                          :238
-    const double rkv = rcp_f64(k * v);       // one reciprocal serves 1/k and 1/v
-    const double inv_k = rkv * v, inv_v = rkv * k;
-    const double rden = y * inv_v;           // 1/(v sqrt t)
-    const double lg = log_f64(s * inv_k, tab);  // log(s/k)                   :226
-    const double drift = fma(0.5 * v, v, r); // r + v^2/2                     :231-234
-    const double d1 = fma(drift, t, lg) * rden;  //                           :235-239
-    const double d2 = d1 - den;              //                               :240
-    const double fv = k * exp_f64(-r * t, tab);  // strike exp(-r t)          :248
+    const double kv = k * v;
+    const double R = rsqrt_f64((kv * kv) * t);   // 1/(k v sqrt t)
+    const double rden = R * k;                   // 1/(v sqrt t)
+    const double y = rden * v;                   // 1/sqrt t
+    const double sq = t * y;                     // sqrt t                        :224
+    const double den = v * sq;                   // xDen                          :238
+    const double sk = s * (R * den);             // s/k
+    const double lg = log_f64(sk, tab);          // log(s/k)                      :226
+    const double drift = fma(0.5 * v, v, r);     // r + v^2/2                     :231-234
+    const double d1 = fma(drift, t, lg) * rden;  //                               :235-239
+    const double d2 = d1 - den;                  //                               :240
+    const double rt = r * t;
+    const double fv = k * exp_core_f64(-rt, tab);  // strike exp(-r t)            :248
     const double a1 = fma(fabs(d1), kd(K_CNDF_C), 1.0), a2 = fma(fabs(d2), kd(K_CNDF_C), 1.0);
-    const double rab = rcp_f64(a1 * a2);     // one reciprocal serves both CNDF arguments   :156-158
-    const double w1 = cndf_tail_f64(d1, rab * a2, tab);
-    const double w2 = cndf_tail_f64(d2, rab * a1, tab);
-    const bool put = otype != 0;
-    // N(x) = w for x < 0 and 1-w otherwise; a put needs N(-x)                :249-255
-    const double x1 = ((d1 < 0.0) != put) ? w1 : 1.0 - w1;
-    const double x2 = ((d2 < 0.0) != put) ? w2 : 1.0 - w2;
-    const double c = fma(s, x1, -(fv * x2));
-    // Domain of the blocks above: t, k*v and s/k positive normal numbers well inside the exponent range
-    // (biased exponent in [0x100, 0x6ff], i.e. 2^-767 .. 2^768); the product a1*a2 = (1 + c|d1|)(1 + c|d2|) fed to the
-    // shared reciprocal finite (it overflows for v below ~1e-154, where |d| ~ 1/v: rcp(inf) = 0 and 0 * inf = NaN
-    // where the reference still returns the intrinsic value); and |r t| < 2^9, so exp_f64's exponent arithmetic cannot
-    // wrap (the reference returns inf / NaN there, exp_f64 a finite number).  Integer range checks on the high
-    // words; everything else (t = 0, v = 0, s <= 0, NaN, inf, denormals, overflow) is left to the IEEE-order path.
-    const uint32_t LO = 0x10000000u, SPAN = 0x60000000u;
-    const uint32_t hi_a = (uint32_t)(to_bits(a1 * a2) >> 32), hi_rt = (uint32_t)(to_bits(r * t) >> 32) & 0x7fffffffu;
-    *ok = ((uint32_t)(to_bits(t) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(k * v) >> 32) - LO < SPAN) &&
-          ((uint32_t)(to_bits(s * inv_k) >> 32) - LO < SPAN) && (hi_a < 0x6ff00000u) && (hi_rt < 0x40800000u);
-    return put ? -c : c;
+    const double a12 = a1 * a2;
+    const double rab = rcp_f64(a12);             // one reciprocal serves both CNDF arguments   :156-158
+    const double g = s * exp_core_f64((-0.5 * d1) * d1, tab);  // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
+    const double P1 = cndf_poly_f64(rab * a2), P2 = cndf_poly_f64(rab * a1);
+    // N(x) = tail w for x < 0 and 1 - w otherwise; a put needs N(-x): the tail itself is wanted when sign(d) != put.   :249-255
+    const uint64_t SIGN = 0x8000000000000000ull;
+    const uint64_t putm = otype != 0 ? SIGN : 0ull;
+    const uint64_t m1 = (to_bits(d1) ^ putm) & SIGN, m2 = (to_bits(d2) ^ putm) & SIGN;  // SIGN: the tail itself
+    const double t1 = from_bits(to_bits(P1) ^ m1 ^ SIGN);   // +P1 for the tail, -P1 for 1 - tail
+    const double t2 = from_bits(to_bits(P2) ^ m2 ^ SIGN);
+    const uint64_t all1 = (uint64_t)((int64_t)m1 >> 63), all2 = (uint64_t)((int64_t)m2 >> 63);
+    const double bs = from_bits(to_bits(s) & ~all1);        // s when N1 = 1 - w1, else 0
+    const double bf = from_bits(to_bits(fv) & ~all2);       // fv when N2 = 1 - w2, else 0
+    const double c = fma(g, t1 - t2, bs - bf);
+    // Domain of the blocks above (integer range checks on the high words; everything else -- t = 0, v = 0, s <= 0,
+    // NaN, inf, denormals, overflow -- is left to the IEEE-order path, which reproduces the reference's inf/NaN results):
+    //   t, k v and s/k positive normal numbers in [2^-255, 2^256): (k v)^2 t stays normal;
+    //   |d1| < 37: exp(-d1^2/2) has not underflowed, so expressing the second tail through it loses nothing
+    //              (inside the inputgen range |d1| <= 32);
+    //   a1 a2 = (1 + c|d1|)(1 + c|d2|) finite: the shared reciprocal is not 0 * inf (v below ~1e-154);
+    //   |r t| < 512: the exponent arithmetic of exp_core_f64 cannot wrap (the reference returns inf / NaN there).
+    const uint32_t LO = 0x30000000u, SPAN = 0x20000000u;
+    const uint32_t hi_d1 = (uint32_t)(to_bits(d1) >> 32) & 0x7fffffffu, hi_rt = (uint32_t)(to_bits(rt) >> 32) & 0x7fffffffu;
+    *ok = ((uint32_t)(to_bits(t) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(kv) >> 32) - LO < SPAN) &&
+          ((uint32_t)(to_bits(sk) >> 32) - LO < SPAN) && (hi_d1 < 0x40428000u) && ((uint32_t)(to_bits(a12) >> 32) < 0x6ff00000u) &&
+          (hi_rt < 0x40800000u);
+    return from_bits(to_bits(c) ^ putm);   // put: fv N(-d2) - s N(-d1) = -(s N(-d1) - fv N(-d2))
 }
 
 }  // namespace bsm

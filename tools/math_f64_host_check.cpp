@@ -59,6 +59,15 @@ int main(int argc, char **argv)
         w_exp_abs = fmax(w_exp_abs, ulps(bsm::exp_f64(xs, TAB), expl((long double)xs)));
     }
     printf("rcp %.3f\nrsqrt %.3f\nlog %.3f\nexp %.3f\nexp_small %.3f\n", w_rcp, w_rsq, w_log, w_exp, w_exp_abs);
+    // the unguarded exp core, both signs, |x| < 500
+    double w_pp = 0, w_pn = 0;
+    for (int i = 0; i < N; i++) {
+        double x = (u01(rng) - 0.5) * (i % 4 == 0 ? 1000.0 : 1.0);
+        double ep = bsm::exp_core_f64(x, TAB), en = bsm::exp_core_f64(-x, TAB);
+        w_pp = fmax(w_pp, ulps(ep, expl((long double)x)));
+        w_pn = fmax(w_pn, ulps(en, expl(-(long double)x)));
+    }
+    printf("exp_pair_pos %.3f\nexp_pair_neg %.3f\n", w_pp, w_pn);
     printf("exp_below_-708 %g\nexp_0 %.17g\nlog_1 %.17g\n", bsm::exp_f64(-709.5, TAB), bsm::exp_f64(0.0, TAB), bsm::log_f64(1.0, TAB));
     // log(x) for x within 1e-3 of 1, error relative to the result
     double w_log1 = 0;

@@ -25,6 +25,9 @@ CONFIGS = {
     "tma": [(4, "fast", 1, 256, 4, 0), (4, "fast", 1, 256, 0, 4), (4, "fast", 1, 256, 1, 4), (4, "fast", 1, 256, 4, 2), (4, "fast", 1, 256, 0, 6),
             (4, "ieee", 1, 256, 0, 0), (4, "ieee", 1, 256, 0, 4),
             (8, "fast", 1, 256, 0, 1), (8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 1, 4), (8, "fast", 1, 256, 0, 6), (8, "ieee", 1, 256, 0, 4)],
+    "fp64r2": [(8, "fast", 1, 256, 0, 1), (8, "fast", 1, 224, 0, 1), (8, "fast", 1, 192, 0, 1), (8, "fast", 1, 160, 0, 1), (8, "fast", 1, 128, 0, 1),
+               (8, "fast", 1, 96, 0, 1), (8, "fast", 1, 64, 0, 1), (8, "fast", 1, 256, 0, 0), (8, "fast", 1, 192, 0, 0), (8, "fast", 1, 128, 0, 0),
+               (8, "fast", 2, 128, 0, 0), (8, "fast", 2, 128, 0, 1), (8, "fast", 2, 256, 0, 1), (8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2)],
     "fp64": [(8, "fast", 1, 256, 0, 0), (8, "fast", 2, 256, 0, 0), (8, "fast", 1, 256, 0, 1), (8, "fast", 1, 128, 0, 1), (8, "fast", 2, 128, 0, 1),
              (8, "fast", 2, 256, 0, 1), (8, "fast", 1, 64, 0, 1), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2),
              (8, "ieee", 1, 256, 0, 0), (8, "ieee", 2, 256, 0, 0), (8, "ieee", 1, 256, 0, 1), (8, "ieee", 1, 128, 0, 1)],
