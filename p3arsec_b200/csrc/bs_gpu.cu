@@ -100,6 +100,7 @@ struct bs_gpu_ctx {
     unsigned flags = 0;
     int math = BS_MATH_FAST;
     int cfg_threads = 0, cfg_blocks_per_sm = 0, unroll = 0, variant = 0;
+    bool tma_wide = false;  // fp64 TMA kernel: 24 consumer warps / 3 stages instead of 16 / 4
     std::vector<Shard> shards;
     void *host[BS_BUF_COUNT] = {nullptr};  // page-aligned anonymous mappings, pinned lazily by the device threads
     size_t host_bytes[BS_BUF_COUNT] = {0};
@@ -200,14 +201,28 @@ int kernel_math(const bs_gpu_ctx *c)
     return c->math;
 }
 bool use_tma(const bs_gpu_ctx *c, bool chk) { return (c->variant & VARIANT_TMA) && !chk && c->math != BS_MATH_REFERENCE; }
-template <typename FP> const void *tma_kernel(int math)
+template <typename FP, int SHAPE> const void *tma_kernel(int math)
 {
-    if (math == bsk::MATH_PROBE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_PROBE>;
-    if (math == BS_MATH_IEEE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_IEEE>;
-    return (const void *)bsk::bs_map_tma<FP, bsk::MATH_FAST>;
+    if (math == bsk::MATH_PROBE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_PROBE, SHAPE>;
+    if (math == BS_MATH_IEEE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_IEEE, SHAPE>;
+    return (const void *)bsk::bs_map_tma<FP, bsk::MATH_FAST, SHAPE>;
 }
-const void *tma_kernel_ptr(const bs_gpu_ctx *c) { return c->fp_bytes == 4 ? tma_kernel<float>(kernel_math(c)) : tma_kernel<double>(kernel_math(c)); }
-size_t tma_smem(const bs_gpu_ctx *c) { return c->fp_bytes == 4 ? bsk::tma_smem_bytes<float>() : bsk::tma_smem_bytes<double>(); }
+// shape of the TMA kernel: fp32 has one; fp64 has the 16-warp / 4-stage and the 24-warp / 3-stage one (tma_wide)
+const void *tma_kernel_ptr(const bs_gpu_ctx *c)
+{
+    if (c->fp_bytes == 4) return tma_kernel<float, 0>(kernel_math(c));
+    return c->tma_wide ? tma_kernel<double, 1>(kernel_math(c)) : tma_kernel<double, 0>(kernel_math(c));
+}
+size_t tma_smem(const bs_gpu_ctx *c)
+{
+    if (c->fp_bytes == 4) return bsk::tma_smem_bytes<float, 0>();
+    return c->tma_wide ? bsk::tma_smem_bytes<double, 1>() : bsk::tma_smem_bytes<double, 0>();
+}
+int tma_threads(const bs_gpu_ctx *c)
+{
+    if (c->fp_bytes == 4) return bsk::tma_threads<float, 0>();
+    return c->tma_wide ? bsk::tma_threads<double, 1>() : bsk::tma_threads<double, 0>();
+}
 KernelF32 pick_f32(const bs_gpu_ctx *c, bool chk) { return pick_kernel<float>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 KernelF64 pick_f64(const bs_gpu_ctx *c, bool chk) { return pick_kernel<double>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 const void *kernel_ptr(const bs_gpu_ctx *c, bool chk)
@@ -265,7 +280,7 @@ cudaError_t launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (float *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const float *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        if (use_tma(c, chk)) return launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
+        if (use_tma(c, chk)) return launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, tma_threads(c), tma_smem(c));
         return launch_kernel(c, s, (const void *)pick_f32(c, chk), blocks, &a, &count, &ec, allow_pdl);
     } else {
         bsk::StreamsF64 a;
@@ -277,7 +292,7 @@ cudaError_t launch_map_range(bs_gpu_ctx *c, Shard &s, bool chk, int record, size
         a.otype = (const int *)s.d[BS_BUF_OTYPE] + first;
         a.prices = (double *)s.d[BS_BUF_PRICES] + first;
         a.refval = s.d[BS_BUF_DGREFVAL] ? (const double *)s.d[BS_BUF_DGREFVAL] + first : nullptr;
-        if (use_tma(c, chk)) return launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, bsk::TMA_THREADS, tma_smem(c));
+        if (use_tma(c, chk)) return launch_kernel(c, s, tma_kernel_ptr(c), s.tma_blocks, &a, &count, &ec, allow_pdl, tma_threads(c), tma_smem(c));
         return launch_kernel(c, s, (const void *)pick_f64(c, chk), blocks, &a, &count, &ec, allow_pdl);
     }
 }
@@ -370,7 +385,7 @@ void do_setup(bs_gpu_ctx *c, Shard &s)
     if (c->variant & VARIANT_TMA) {
         SH_CUDA(cudaFuncSetAttribute(tma_kernel_ptr(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem(c)));
         int fit = 0;
-        SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, tma_kernel_ptr(c), bsk::TMA_THREADS, tma_smem(c)));
+        SH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, tma_kernel_ptr(c), tma_threads(c), tma_smem(c)));
         if (fit < 1) fit = 1;
         if (c->cfg_blocks_per_sm > 0) fit = std::min(fit, c->cfg_blocks_per_sm);
         s.tma_blocks = s.sm_count * fit;
@@ -1056,10 +1071,16 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     c->unroll = cfg->unroll ? cfg->unroll : (sustained ? 2 : 1);
     if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST && !sustained) c->cfg_blocks_per_sm = 4;
     c->variant = cfg->variant;
-    // fp64 is instruction-bound: software-pipelined loads (+10 % on B200, profiles/r01_tune_repeat_fp64.txt) unless
-    // the caller chose a geometry/variant explicitly
+    {
+        const char *w = getenv("BS_GPU_TMA_WIDE");  // measurement knob for the fp64 TMA kernel's shape
+        c->tma_wide = c->fp_bytes == 8 && w && *w == '1';
+    }
+    // fp64 (unless the caller chose a geometry/variant explicitly): the fast-math kernel takes its inputs through the
+    // bulk-copy ring (bs_map_tma: 81.0 us per 10M options = 6.42 TB/s against 85.9 us with software-pipelined LDG.128
+    // and 84.3 us for the LDG traffic probe itself, profiles/r02_tune_fp64.txt); ERR_CHK runs, which the TMA kernel
+    // does not implement, use the software-pipelined LDG kernel.
     if (c->fp_bytes == 8 && !cfg->variant && !cfg->unroll && !cfg->threads_per_block && !cfg->blocks_per_sm && c->math == BS_MATH_FAST)
-        c->variant = VARIANT_PIPE;
+        c->variant = VARIANT_PIPE | VARIANT_TMA;
 
     c->want_gpus = cfg->num_gpus;
     if (cfg->devices) c->want_devices.assign(cfg->devices, cfg->devices + cfg->num_gpus);

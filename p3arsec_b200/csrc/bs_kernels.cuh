@@ -542,24 +542,29 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <typename FP> struct TmaCfg;
-template <> struct TmaCfg<float> { enum { TILE = 2048, STAGES = 4 }; };   // 6 x 8 KB per stage; 192 KB per CTA, 1 CTA per SM
-template <> struct TmaCfg<double> { enum { TILE = 1024, STAGES = 4 }; };  // 5 x 8 KB + 4 KB per stage; 176 KB per CTA
-enum { TMA_CONSUMERS = 512, TMA_THREADS = TMA_CONSUMERS + 32 };
+// SHAPE 0: 16 consumer warps, 4 stages.  SHAPE 1 (fp64 only; the fp32 entry is an alias of shape 0): 24 consumer warps, 3 stages --
+// the fp64 math is issue-bound with long dependent DFMA chains, so more resident warps per scheduler hide more of its
+// fixed-latency stalls; registers are then capped at 80 per thread by the launch bounds.
+template <typename FP, int SHAPE> struct TmaCfg;
+template <int SHAPE> struct TmaCfg<float, SHAPE> { enum { TILE = 2048, STAGES = 4, CONSUMERS = 512 }; };  // 6 x 8 KB per stage; 192 KB per CTA, 1 CTA per SM
+template <> struct TmaCfg<double, 0> { enum { TILE = 1024, STAGES = 4, CONSUMERS = 512 }; };              // 5 x 8 KB + 4 KB per stage; 176 KB per CTA
+template <> struct TmaCfg<double, 1> { enum { TILE = 1536, STAGES = 3, CONSUMERS = 768 }; };              // 66 KB per stage; 198 KB per CTA
 
-template <typename FP> __host__ __device__ constexpr size_t tma_stage_bytes() { return (size_t)TmaCfg<FP>::TILE * (5 * sizeof(FP) + sizeof(int)); }
-template <typename FP> __host__ __device__ constexpr size_t tma_smem_bytes()
+template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_stage_bytes() { return (size_t)TmaCfg<FP, SHAPE>::TILE * (5 * sizeof(FP) + sizeof(int)); }
+template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_smem_bytes()
 {
-    return tma_stage_bytes<FP>() * TmaCfg<FP>::STAGES + 2 * TmaCfg<FP>::STAGES * sizeof(uint64_t) + 128 +
+    return tma_stage_bytes<FP, SHAPE>() * TmaCfg<FP, SHAPE>::STAGES + 2 * TmaCfg<FP, SHAPE>::STAGES * sizeof(uint64_t) + 128 +
            ((sizeof(FP) == 8) ? bsm::TAB_DOUBLES * sizeof(double) : 0);
 }
+template <typename FP, int SHAPE> __host__ __device__ constexpr int tma_threads() { return TmaCfg<FP, SHAPE>::CONSUMERS + 32; }
 
-template <typename FP, int MATH>
-__global__ void __launch_bounds__(TMA_THREADS, 1) bs_map_tma(Streams<FP> a, size_t n, ErrChk ec)
+template <typename FP, int MATH, int SHAPE>
+__global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_tma(Streams<FP> a, size_t n, ErrChk ec)
 {
     typedef typename VT<FP>::vec vec;
     typedef typename VT<FP>::ivec ivec;
-    enum { LANES = VT<FP>::LANES, TILE = TmaCfg<FP>::TILE, STAGES = TmaCfg<FP>::STAGES, GROUPS = TILE / LANES };
+    enum { LANES = VT<FP>::LANES, TILE = TmaCfg<FP, SHAPE>::TILE, STAGES = TmaCfg<FP, SHAPE>::STAGES, GROUPS = TILE / LANES,
+           TMA_CONSUMERS = TmaCfg<FP, SHAPE>::CONSUMERS };
     constexpr unsigned FP_TILE_BYTES = TILE * sizeof(FP), OT_TILE_BYTES = TILE * sizeof(int);
     constexpr unsigned STAGE_BYTES = 5 * FP_TILE_BYTES + OT_TILE_BYTES;
     extern __shared__ __align__(128) unsigned char smem[];
