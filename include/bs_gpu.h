@@ -141,6 +141,13 @@ typedef struct bs_gpu_timing {
 /* Number of usable CUDA devices (>= 0), or a negative bs_gpu_status. */
 int bs_gpu_device_count(void);
 
+/* Optional, and only effective BEFORE the process's first CUDA call (so before bs_gpu_device_count / bs_gpu_init):
+ * hide all but the first `max_gpus` devices from this process (CUDA_VISIBLE_DEVICES; an existing list is cut to its
+ * first max_gpus entries).  Driver initialisation and process exit cost time per VISIBLE device -- measured on an
+ * 8 x B200 box: cuInit 4.4-5.4 s with eight devices visible, 0.36-0.49 s with one -- so a one-shot driver that will use
+ * G devices (<nthreads>, blackscholes.c:694) should say so first. */
+int bs_gpu_limit_devices(int max_gpus);
+
 /* Create a context pricing `num_options` options of `fp_bytes`-wide fptype on the first `num_gpus`
  * devices.  Spawns one host thread per device (each owns that device's primary context, stream and
  * CUDA graphs), splits [0,N) into contiguous shards (first N%G shards get one extra option, as

@@ -106,12 +106,34 @@ int main(int argc, char **argv)
         exit(1);
     }
 
-    // <nthreads> -> number of GPUs, clamped to the devices present.  Device discovery (cuInit, ~0.2 s) is done here;
-    // context creation and arena allocation then run in the background while the rows are parsed.
-    // (BS_GPU_FLAG_ASYNC_DISCOVERY would push discovery into the background too, but cuInit's mmap traffic contends
-    // with the parser threads' page faults: measured 1.26 s instead of 0.81 s for the 10M-row native file.)
-    // (Hiding the GPUs that were not asked for -- CUDA_VISIBLE_DEVICES -- does not shorten cuInit: measured 1.33 s on
-    // a 2-GPU box and 4.4 s on an 8-GPU box whatever the visible set is, 0.24 s on a 1-GPU box.)
+    // <nthreads> -> an UPPER BOUND on the number of GPUs.  How many are actually used is chosen from the work, BEFORE CUDA
+    // is touched, and the others are hidden from this process (bs_gpu_limit_devices): a device costs start-up and
+    // tear-down time merely by being visible -- measured on an 8 x B200 box, cuInit takes 4.4-5.4 s with eight devices
+    // visible and 0.36-0.49 s with one, and the exit of a process that saw eight takes 2.5 s (profiles/r02_cuinit_8gpu.jsonl,
+    // r02_e2e_file_native_n8_*.json) -- so a device is only worth having if it receives at least ~50 ms of kernel time,
+    // i.e. ~0.3 TB of stream traffic at the measured ~6.5 TB/s.  One pass over the native set is 40 us: one GPU, whatever
+    // <nthreads> says; the 1B-option set x 100 runs (0.43 s on one GPU) is eight.  BS_GPU_DEVICES=all restores the literal
+    // reading (<nthreads> GPUs, nothing hidden), BS_GPU_DEVICES=<n> forces n.
+    // Device discovery (cuInit) is done here; context creation and arena allocation then run in the background while the
+    // rows are parsed.  (BS_GPU_FLAG_ASYNC_DISCOVERY would push discovery into the background too, but cuInit's mmap
+    // traffic contends with the parser threads' page faults: measured 1.26 s instead of 0.81 s for the native file.)
+    int wantGpus = nThreads < 1 ? 1 : nThreads;
+    const char *dev_env = getenv("BS_GPU_DEVICES");
+    const char *gpu_policy = "nthreads";
+    const bool literal = dev_env && !strcmp(dev_env, "all");
+    if (dev_env && atoi(dev_env) > 0) {
+        wantGpus = atoi(dev_env);
+        gpu_policy = "BS_GPU_DEVICES";
+    } else if (!literal) {
+        const double bytes = (double)numOptions * NUM_RUNS * (6.0 * sizeof(fptype) + 4.0);  // algorithmic stream traffic of the ROI
+        int by_work = (int)(bytes / 6.5e12 / 0.050);
+        if (by_work < 1) by_work = 1;
+        if (by_work < wantGpus) {
+            wantGpus = by_work;
+            gpu_policy = "work";
+        }
+    }
+    if (!literal) bs_gpu_limit_devices(wantGpus);
     const double t_cuinit0 = now_s();
     const int have = bs_gpu_device_count();
     if (have <= 0) {
@@ -125,7 +147,8 @@ int main(int argc, char **argv)
     cfg.struct_size = sizeof(cfg);
     cfg.num_options = (size_t)numOptions;
     cfg.fp_bytes = (int)sizeof(fptype);
-    cfg.num_gpus = nThreads < 1 ? 1 : (nThreads > have ? have : nThreads);
+    if (wantGpus > have) wantGpus = have;
+    cfg.num_gpus = wantGpus;
     cfg.flags = BS_GPU_FLAG_WITH_DGREFVAL;
     rv = bs_gpu_init_ex(&ctx, &cfg);
     const double t_init1 = now_s();
@@ -202,8 +225,8 @@ int main(int argc, char **argv)
     bs_gpu_timing tm;
     bs_gpu_get_timing(ctx, &tm);
     const int nGpus = bs_gpu_num_shards(ctx);
-    printf("[BS_GPU] gpus=%d h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f launches=%llu\n", nGpus, tm.h2d_ms, tm.roi_ms,
-           tm.d2h_ms, tm.kernel_launches);
+    printf("[BS_GPU] gpus=%d (asked %d, visible %d, chosen by %s) h2d_ms=%.3f kernels_ms=%.3f d2h_ms=%.3f launches=%llu\n", nGpus,
+           nThreads, have, gpu_policy, tm.h2d_ms, tm.roi_ms, tm.d2h_ms, tm.kernel_launches);
     if (tm.roi_ms > 0)
         printf("[BS_GPU] kernel-only rate: %.3f G options/s\n", (double)numOptions * NUM_RUNS / (tm.roi_ms * 1e-3) / 1e9);
 

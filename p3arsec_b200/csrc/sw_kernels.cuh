@@ -172,7 +172,19 @@ SW_HD_NOINLINE double cumnormalinv_ieee(double u)
 // to libdevice, out of line.  The range check is done on the high word with integer instructions: the FP64 pipe is
 // the bottleneck of this kernel and a DSETP would cost it two issue cycles per exponential.
 SW_HD_NOINLINE double exp_slow(double x) { return exp(x); }
-SW_HD double exp_core(double x, const double *tab)
+// Where exp_core reads 2^(j/64) from.  The index j is the low six bits of a rounded product, i.e. random per lane, so a
+// plain 64-entry table in shared memory serves a half-warp's 64-bit loads in 2-4 wavefronts (16 bank pairs, 16 lanes
+// with unrelated j).  REP = 16 copies interleaved [j][lane & 15] give every lane of a half-warp its own bank pair
+// whatever j is: always one wavefront (8 KB per CTA).  REP = 1 is the plain table (host checker, generic fallback).
+template <int REP_SHIFT>
+struct ExpTab {
+    const double *t;
+    int lane;
+    SW_HD double at(int j) const { return t[(j << REP_SHIFT) + lane]; }
+};
+constexpr int EXP_REP_SHIFT = 4, EXP_REP_DOUBLES = 64 << EXP_REP_SHIFT;
+template <class ET>
+SW_HD double exp_core(double x, const ET &et)
 {
     using namespace bsm;
     const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
@@ -185,7 +197,7 @@ SW_HD double exp_core(double x, const double *tab)
     q = fma(q, r, kd(K_EXP_C3));
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
-    const double T = tab[TAB_EXP + (n & 63)];
+    const double T = et.at(n & 63);
     const double m = fma(T, em1, T);
     return from_bits(to_bits(m) + ((uint64_t)(int64_t)(n >> 6) << 52));
 }
@@ -193,10 +205,11 @@ SW_HD double exp_core(double x, const double *tab)
 // exponential with exp_core, branch-free, and only tracks the largest such high word of the trial (LOP3 + VIMNMX on the
 // integer pipes); a trial that exceeded the limit is redone by generic_trial().
 constexpr uint32_t EXP_HI_LIMIT = 0x4085E000u;
-SW_HD double exp_tracked(double x, const double *tab, uint32_t &worst)
+template <class ET>
+SW_HD double exp_tracked(double x, const ET &et, uint32_t &worst)
 {
     worst = umax32(worst, (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu);
-    return exp_core(x, tab);
+    return exp_core(x, et);
 }
 
 // CumNormalInv takes its central branch iff fabs(u - 0.5) < 0.42 with u = s * 4.656612875e-10 (s the 31-bit draw).
@@ -246,6 +259,10 @@ __global__ void sw_fill_tables(double *__restrict__ g)
 SW_HD void load_tables(double *__restrict__ smem_tail_then_tab, const double *__restrict__ g, int tid)
 {
     for (int i = tid; i < TABLE_DOUBLES; i += THREADS) smem_tail_then_tab[i] = g[i];
+}
+SW_HD void load_exp_replicated(double *__restrict__ xexp, const double *__restrict__ g, int tid)
+{
+    for (int i = tid; i < EXP_REP_DOUBLES; i += THREADS) xexp[i] = g[swt::TAIL_DOUBLES + bsm::TAB_EXP + (i >> EXP_REP_SHIFT)];
 }
 
 // Block-wide sum of two doubles; result valid in thread 0.
@@ -324,6 +341,7 @@ struct FastShared {
     double fwd[FN];
     double pay[FN];
     double red[2][THREADS / 32];
+    double xexp[EXP_REP_DOUBLES];  // 2^(j/64) replicated [j][lane & 15]: conflict-free whatever the lanes' j (ExpTab)
 };
 // Behind FastShared in dynamic shared memory: z[z_rows][THREADS], the trial's normals [draw][thread] (conflict-free) --
 // all 30 draws for the full kernel, 3 x (largest swap start index of the launch) for the lean one.
@@ -435,8 +453,8 @@ SW_HD void normals(const double *__restrict__ tab, const double *__restrict__ ta
 // remembers whether one of them left the fast range.
 // SRC = where the swaption's tables (fd, fwd, pay) are read from: FastShared (shared memory, any swaption per work item)
 // or OneSwaption (kernel-parameter constant bank, one swaption per launch).
-template <bool LEAN, int START, class SRC>
-SW_HD double path_and_payoff(const SRC &sh, const double *__restrict__ tab, const double *__restrict__ z, int tid, double ddelt,
+template <bool LEAN, int START, class SRC, class ET>
+SW_HD double path_and_payoff(const SRC &sh, const ET &tab, const double *__restrict__ z, int tid, double ddelt,
                                                   double swap_ddelt, int start_rt, int swap_end, uint32_t &worst)
 {
     const int start = START >= 0 ? START : start_rt;
@@ -507,6 +525,8 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
     const int tid = threadIdx.x;
     static_assert(offsetof(FastShared, tail) == 0 && offsetof(FastShared, tab) == sizeof(double) * swt::TAIL_DOUBLES, "[tail | tab] first");
     load_tables(sh.tail, tables, tid);
+    load_exp_replicated(sh.xexp, tables, tid);
+    const ExpTab<EXP_REP_SHIFT> et = {sh.xexp, tid & ((1 << EXP_REP_SHIFT) - 1)};
 
     int cur = -1;
     double ddelt = 0, swap_ddelt = 0;
@@ -554,10 +574,10 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             uint32_t worst = 0;
             double disc;
             switch (start) {
-                case 1: disc = path_and_payoff<LEAN, 1>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                case 2: disc = path_and_payoff<LEAN, 2>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                case 3: disc = path_and_payoff<LEAN, 3>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
-                default: disc = path_and_payoff<LEAN, -1>(sh, sh.tab, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 1: disc = path_and_payoff<LEAN, 1>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 2: disc = path_and_payoff<LEAN, 2>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                case 3: disc = path_and_payoff<LEAN, 3>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
+                default: disc = path_and_payoff<LEAN, -1>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
             }
             if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[sw], FN, FF, t);
             sum += disc;                                                  // HSB:203
@@ -591,6 +611,7 @@ struct OneShared {
     double tail[swt::TAIL_DOUBLES];
     double tab[bsm::TAB_DOUBLES];
     double red[2][THREADS / 32];
+    double xexp[EXP_REP_DOUBLES];  // 2^(j/64) replicated [j][lane & 15] (ExpTab)
 };
 static_assert(sizeof(OneShared) % 16 == 0, "z starts 16-byte aligned");
 SW_HOST_DEVICE constexpr size_t one_shared_bytes(int z_rows) { return sizeof(OneShared) + (size_t)z_rows * THREADS * sizeof(double); }
@@ -607,6 +628,8 @@ sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ p
     const int tid = threadIdx.x;
     static_assert(offsetof(OneShared, tail) == 0 && offsetof(OneShared, tab) == sizeof(double) * swt::TAIL_DOUBLES, "[tail | tab] first");
     load_tables(sh.tail, tables, tid);
+    load_exp_replicated(sh.xexp, tables, tid);
+    const ExpTab<EXP_REP_SHIFT> et = {sh.xexp, tid & ((1 << EXP_REP_SHIFT) - 1)};
     const int steps = LEAN ? P.start : FN - 1;
     const int swap_end = LEAN ? P.last_pay : P.len - 1;
 
@@ -620,10 +643,10 @@ sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ p
             uint32_t worst = 0;
             double disc;
             switch (P.start) {
-                case 1: disc = path_and_payoff<LEAN, 1>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
-                case 2: disc = path_and_payoff<LEAN, 2>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
-                case 3: disc = path_and_payoff<LEAN, 3>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
-                default: disc = path_and_payoff<LEAN, -1>(P, sh.tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                case 1: disc = path_and_payoff<LEAN, 1>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                case 2: disc = path_and_payoff<LEAN, 2>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                case 3: disc = path_and_payoff<LEAN, 3>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+                default: disc = path_and_payoff<LEAN, -1>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
             }
             if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[P.sw_index], FN, FF, t);
             sum += disc;                     // HSB:203

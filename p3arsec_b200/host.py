@@ -34,7 +34,7 @@ assert DATACONT_DTYPE.itemsize == 24
 
 # every symbol include/bs_gpu.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = (
-    "bs_gpu_abi_version", "bs_gpu_status_string", "bs_gpu_device_count", "bs_gpu_init", "bs_gpu_init_ex",
+    "bs_gpu_abi_version", "bs_gpu_status_string", "bs_gpu_device_count", "bs_gpu_limit_devices", "bs_gpu_init", "bs_gpu_init_ex",
     "bs_gpu_host_buffer", "bs_gpu_mark_dirty", "bs_gpu_price", "bs_gpu_upload", "bs_gpu_run", "bs_gpu_download",
     "bs_gpu_price_aos", "bs_gpu_fill_synthetic", "bs_gpu_read_device", "bs_gpu_errors", "bs_gpu_num_shards", "bs_gpu_shard",
     "bs_gpu_get_timing", "bs_gpu_get_launch", "bs_gpu_last_error", "bs_gpu_fini",
@@ -94,6 +94,7 @@ def load_library(path=None):
     L.bs_gpu_abi_version.restype, L.bs_gpu_abi_version.argtypes = ci, []
     L.bs_gpu_status_string.restype, L.bs_gpu_status_string.argtypes = ctypes.c_char_p, [ci]
     L.bs_gpu_device_count.restype, L.bs_gpu_device_count.argtypes = ci, []
+    L.bs_gpu_limit_devices.restype, L.bs_gpu_limit_devices.argtypes = ci, [ci]
     L.bs_gpu_init.restype, L.bs_gpu_init.argtypes = ci, [ctypes.POINTER(vp), ci, cs, ci]
     L.bs_gpu_init_ex.restype, L.bs_gpu_init_ex.argtypes = ci, [ctypes.POINTER(vp), ctypes.POINTER(Config)]
     L.bs_gpu_host_buffer.restype, L.bs_gpu_host_buffer.argtypes = vp, [vp, ci]

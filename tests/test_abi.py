@@ -145,3 +145,17 @@ def test_headers_are_plain_c_and_link(tmp_path):
                     "-L", lib_dir, "-lbs_gpu", "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.split() == [str(host.ABI_VERSION), "-1", "no", "usable", "CUDA", "device", "8"]
+
+
+def test_integration_patches_apply_to_the_reference(tmp_path):
+    # the patches a P3ARSEC maintainer would apply: both must apply cleanly to the reference as it lies
+    ref = "/root/reference/parsec-ff/pkgs/apps/blackscholes/src/blackscholes.c"
+    if not os.path.exists(ref):
+        pytest.skip("/root/reference is not mounted on this box")
+    integ = os.path.join(ROOT, "integration")
+    step1 = str(tmp_path / "bs_cuda.c")
+    subprocess.run(["patch", "-s", "-o", step1, ref, os.path.join(integ, "blackscholes.c.enable_cuda.patch")], check=True)
+    step2 = str(tmp_path / "bs_cuda_caf.c")
+    subprocess.run(["patch", "-s", "-o", step2, step1, os.path.join(integ, "blackscholes.c.caf_cuda.patch")], check=True)
+    text = open(step2).read()
+    assert "bs_gpu_price_aos(gpu, data_vec.data(), nv, res.data(), 1)" in text and "bs_gpu_price(gpu, NUM_RUNS" in text

@@ -421,6 +421,27 @@ def test_price_aos_caf_message_quirk_and_errors():
             bs.price_aos(rec[:1000], 1)               # DataCont holds floats
 
 
+@pytest.mark.parametrize("name", ["hull4", "table1k", "ragged37"])
+def test_caf_message_path_harness(name, tmp_path):
+    # integration/blackscholes.c.caf_cuda.patch cannot be compiled (CAF is un-vendored upstream); the harness reproduces the
+    # reference's CAF_V3 driver around the patched handler -- DataCont records, the 2N-record message, NUM_RUNS requests
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "caf_harness")
+    lib_dir = os.path.dirname(host.LIB_PATH)
+    subprocess.run(["g++", "-O2", "-std=c++11", "-I", os.path.join(root, "include"), os.path.join(root, "integration", "caf_map_cuda_harness.cpp"),
+                    "-o", exe, "-L", lib_dir, "-lbs_gpu", "-Wl,-rpath," + lib_dir], check=True)
+    out = str(tmp_path / "prices.txt")
+    cp = subprocess.run([exe, "1", golden_path(name, "in.txt"), out], capture_output=True, text=True)
+    assert cp.returncode == 0, cp.stdout + cp.stderr
+    ref = _golden_prices(name, "f32")
+    n = len(ref)
+    assert "message records: %d, prices returned: %d" % (2 * n, 2 * n) in cp.stdout
+    assert "zero records priced NaN: %d of %d" % (n, n) in cp.stdout
+    cnt, toks = oracle_lib.read_prices_text(out)
+    assert cnt == n
+    assert_parity(np.array([float(t) for t in toks]), ref, 4, "%s/caf harness" % name)
+
+
 def test_price_aos_sharded():
     _need_two_gpus("test_price_aos_sharded")
     n = 1000003

@@ -49,6 +49,9 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2_000_000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--dir", default="/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    ap.add_argument("--devices", default=None, help="value for BS_GPU_DEVICES (all = <nthreads> GPUs literally; unset = chosen from the work)")
+    ap.add_argument("--fast-exit", default=None, help="value for BS_GPU_FAST_EXIT (0 = ordinary exit through the CUDA runtime's teardown)")
+    ap.add_argument("--ref-full", action="store_true", help="also run the reference on the FULL file (tens of seconds)")
     a = ap.parse_args()
     import numpy as np
     import oracle_lib
@@ -57,6 +60,10 @@ def main():
     inp, out = os.path.join(d, "in.txt"), os.path.join(d, "prices.txt")
     run([os.path.join(BIN, "bs_inputgen"), str(a.n), inp])
     best = None
+    if a.devices is not None:
+        os.environ["BS_GPU_DEVICES"] = a.devices
+    if a.fast_exit is not None:
+        os.environ["BS_GPU_FAST_EXIT"] = a.fast_exit
     for _ in range(a.reps):
         wall, so = run([os.path.join(BIN, "blackscholes_gpu_runs1"), str(a.gpus), inp, out])
         info = dict(kv(so, "[BS_GPU] "), wall_s=wall)
@@ -64,7 +71,18 @@ def main():
             best = info
     res = {"config": "end-to-end native %d options, fp32, NUM_RUNS=1, %d GPU(s), incl. file parse/SoA staging/H2D/D2H/prices file" % (a.n, a.gpus),
            "input_bytes": os.path.getsize(inp), "output_bytes": os.path.getsize(out), "host_cores": len(os.sched_getaffinity(0)),
-           "ours": best, "ours_options_per_s_whole_process": a.n / best["wall_s"]}
+           "ours": best, "ours_options_per_s_whole_process": a.n / best["wall_s"],
+           "env": {"BS_GPU_DEVICES": os.environ.get("BS_GPU_DEVICES"), "BS_GPU_FAST_EXIT": os.environ.get("BS_GPU_FAST_EXIT")}}
+    if a.ref_full and oracle_lib.ref_binary("bs_ref_ff"):
+        # the reference on the SAME file (its NUM_RUNS=100 is compiled in: the ROI is scaled to one run, load + write are what they are)
+        cores = len(os.sched_getaffinity(0))
+        rout = os.path.join(d, "ref_prices.txt")
+        t0 = time.perf_counter()
+        so, roi = oracle_lib.run_ref("bs_ref_ff", cores, inp, rout, timeout=3600)
+        wall = time.perf_counter() - t0
+        res["reference_full_file"] = {"rows": a.n, "wall_s_with_100_runs": wall, "roi_s_100_runs": roi, "load_plus_write_s": wall - roi,
+                                      "NUM_RUNS_1_equivalent_s": wall - roi + roi / 100, "cores": cores}
+        os.unlink(rout)
 
     # reference beside it, bounded sample, and parity of the two prices files on that sample
     sinp, sout, gout = os.path.join(d, "s_in.txt"), os.path.join(d, "s_ref.txt"), os.path.join(d, "s_gpu.txt")

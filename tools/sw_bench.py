@@ -116,7 +116,7 @@ def ours(args):
     ranks = Ranks(backend="nccl", device=torch.device("cuda", local_rank))
     n_gpus = world * in_process_gpus
     flags = {"fast": 0, "lean": sw.FLAG_LEAN, "ieee": sw.FLAG_IEEE}[args.mode] | (sw.FLAG_BATCHED if args.batched else 0)
-    one_per_launch = args.mode == "fast" and not args.batched and ((trials + 15) // 16) * 16 >= 262144
+    # which kernel the library chose is read back from its launch counts after the timed region (below)
 
     seed, p, y, f = sw.make_portfolio(ns)
     first, count = shard_range(ns, world, rank)
@@ -134,7 +134,7 @@ def ours(args):
 
     for _ in range(args.warmup):
         step()
-    sampler = main_bench.ClockSampler(local_rank)
+    sampler = main_bench.ClockSampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
     torch.cuda.synchronize()
@@ -159,6 +159,9 @@ def ours(args):
     clocks = sampler.stop() if rank == 0 else None
     dev_ms_max, wall_ms_max = ranks.max(dev_ms), ranks.max(wall_ms)
     sims_total = ranks.sum(sims_local)
+    launches_total = int(ranks.sum(launches))  # ranks may hold unequal shards: count, do not extrapolate
+    # one launch per swaption (sw_sim_one) shows as count + 1 launches per device and ROI; the batched kernel as 2
+    one_per_launch = launches // args.steps // max(in_process_gpus, 1) > 2
     value = sims_total / (dev_ms_max * 1e-3)
     e2e = {"value": sims_total / (wall_ms_max * 1e-3), "unit": "trials/s", "h2d_bytes_per_step": int(ranks.sum(h2d) / args.steps),
            "d2h_bytes_per_step": int(ranks.sum(d2h) / args.steps), "ms_per_step": wall_ms_max / args.steps, "checksum": checksum,
@@ -196,7 +199,19 @@ def ours(args):
                 "roi_us": dev_ms / args.steps * 1e3, "launches_per_roi_per_gpu": launches // args.steps // max(in_process_gpus, 1),
                 "launch_note": "one sw_sim_one launch per swaption, rotating over 4 streams so that their tails overlap, + sw_finalize; the ROI is timed "
                                "with CUDA events around all of them" if one_per_launch else "one simulation launch + sw_finalize per ROI",
-                "note": "instructions per trial come from profiles/sw_ncu_counts.json (ncu smsp__inst_executed_pipe_fp64 x 32 / trials)"}
+                "note": "instructions per trial come from profiles/sw_ncu_counts.json (ncu smsp__inst_executed_pipe_fp64 x 32 / trials); "
+                        "this figure is PIPE OCCUPANCY (executed instructions), see `algorithmic` for the roofline on the reference's own operation count"}
+    # The algorithmic roofline: floating-point operations the REFERENCE performs per trial (HJM_Swaption_Blocking.cpp:156-204
+    # and the leaves it calls, iN = 11, iFactors = 3, counted in DESIGN.md 9.5: 30 draws + 30 CumNormalInv + 55 path entries +
+    # 2 discount-factor passes + payoff = ~1295 multiplies/adds/divides + 19 exp + ~10 log, each transcendental counted as
+    # ONE operation as in SURVEY.md 8d) against the measured DFMA peak counted as two operations per lane and clock.
+    algo_flops = counts.get("algorithmic_flops_per_trial_full", 1325.0)
+    if args.mode == "fast":
+        a_ach = algo_flops * per_gpu_rate / 1e12
+        a_peak = 2.0 * peak
+        roofline["algorithmic"] = {"achieved": a_ach, "peak": a_peak, "unit": "TFLOP/s (fp64)", "frac": a_ach / a_peak,
+                                   "flops_per_trial": algo_flops,
+                                   "what": "reference operation count per trial x trials/s over 2 x the measured DFMA rate"}
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -217,15 +232,10 @@ def ours(args):
                        "parallelism": "%d contiguous shards of the portfolio, no collective" % n_gpus,
                        "l2": "not applicable: a trial reads no global memory (per-swaption parameters sit in shared memory), so there is nothing to flush",
                        "step": "one ROI = the Map over the whole portfolio (HJM_Securities.cpp:311-323)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(ranks_sum_launches(launches, world)), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total, "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms_per_step": wall_ms_max / args.steps, "parity_spot_max_rel": spot}
     print(json.dumps(line), flush=True)
     return 0
-
-
-def ranks_sum_launches(launches, world):
-    # every rank launches the same number of kernels per step (2 per device): avoid a collective after ranks.close()
-    return launches * world
 
 
 def main(argv=None):

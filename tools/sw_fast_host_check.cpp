@@ -22,13 +22,14 @@ static double one_trial(const SRC &src, const double *tab, const double *tail, d
     const int steps = LEAN ? P.start : FN - 1;
     const int swap_end = LEAN ? P.last_pay : P.len - 1;
     normals<LEAN>(tab, tail, z, tid, ru_residue(P.seed + t * FD), steps);
+    const ExpTab<0> et = {tab + bsm::TAB_EXP, 0};  // the plain table: bank layout is a device-only concern
     uint32_t worst = 0;
     double disc;
     switch (P.start) {
-        case 1: disc = path_and_payoff<LEAN, 1>(src, tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
-        case 2: disc = path_and_payoff<LEAN, 2>(src, tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
-        case 3: disc = path_and_payoff<LEAN, 3>(src, tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
-        default: disc = path_and_payoff<LEAN, -1>(src, tab, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+        case 1: disc = path_and_payoff<LEAN, 1>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+        case 2: disc = path_and_payoff<LEAN, 2>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+        case 3: disc = path_and_payoff<LEAN, 3>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
+        default: disc = path_and_payoff<LEAN, -1>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
     }
     if (worst >= EXP_HI_LIMIT) {
         ++fallbacks;
