@@ -450,6 +450,14 @@ def measure_workload(key, args, host, ranks, torch, rank, local_rank, world, in_
                 floor_ms = (e2e["h2d_bytes_per_step"] / n_gpus) / (cp["h2d_gbs_per_gpu"] * 1e9) * 1e3
                 e2e["h2d_floor_ms_per_step"] = floor_ms
                 e2e["frac_of_h2d_ceiling"] = floor_ms / e2e["ms_per_step"]
+                # inputs in AND prices out, one after the other at the rates measured above.  With one GPU copying the two
+                # directions overlap fully (63 GB/s both ways against 55 one way); with eight, the box's shared uplinks do
+                # not (tools/micro/h2d_ceiling: 21 GB/s per GPU for both directions together against 24.5 in alone,
+                # profiles/r02_h2d_ceiling_8gpu_box.jsonl), so this sum is the step's floor there.
+                if cp["d2h_gbs_per_gpu"]:
+                    both_ms = floor_ms + (e2e["d2h_bytes_per_step"] / n_gpus) / (cp["d2h_gbs_per_gpu"] * 1e9) * 1e3
+                    e2e["copies_in_then_out_ms_per_step"] = both_ms
+                    e2e["frac_of_copies_in_then_out"] = both_ms / e2e["ms_per_step"]
         out["e2e"] = e2e
     bs.close()
 
@@ -621,6 +629,24 @@ def ours(args):
         except Exception as e:
             cpu = {"value": None, "unit": "options/s", "cores": host_cores(), "kind": "unavailable", "sample": str(e)}
 
+    # ---- BASELINE.json's other single-GPU configs, measured in this same run (N = 1, default workload only) ----
+    other = None
+    if single and key == "native" and not args.headline_only:
+        other = {}
+        for ok_key in ("simsmall", "native_fp64"):
+            try:
+                w = measure_workload(ok_key, args, host, ranks, torch, rank, local_rank, world, in_process_gpus, max(3, min(args.steps, 10)), 3)
+                gbs = w["bpo"] * w["n_per_launch"] / (w["ms_per_step"] / NUM_RUNS * 1e-3) / 1e9
+                other[ok_key] = {"workload": w["desc"], "value": w["value"], "unit": "options/s", "ms_per_step": w["ms_per_step"], "steps": w["steps"],
+                                 "us_per_launch": w["ms_per_step"] / NUM_RUNS * 1e3, "hbm_gbs": gbs, "frac_of_measured_peak": gbs / peak,
+                                 "e2e": w["e2e"], "launch": w["launch"], "parity_spot_max_abs": w.get("parity_spot_max_abs"),
+                                 "dtype": "f32" if w["fp_bytes"] == 4 else "f64"}
+                if ok_key == "simsmall" and not args.no_cpu_baseline:
+                    rate, cores, kind, sample, _ = run_cpu_reference(WORKLOADS["simsmall"][0], 3, 1, 4)
+                    other[ok_key]["cpu_baseline"] = {"value": rate, "unit": "options/s", "cores": cores, "kind": kind, "sample": sample}
+            except Exception as e:
+                other[ok_key] = {"error": str(e)}
+
     ranks.close()
     if rank != 0:
         return 0
@@ -628,6 +654,16 @@ def ours(args):
     if world > 1 and not args.headline_only:
         time.sleep(2.0)  # the other ranks are exiting: let their contexts go before GPUs 1..N-1 are used from here
         inproc = inproc_record(world, args, host, max(3, min(args.steps, 5)))
+    # ---- BASELINE.json configs[4]: end-to-end native file -> prices file through the drop-in driver, NUM_RUNS = 1,
+    # <nthreads> = the GPUs of this run (the driver itself decides how many of them the work is worth) ----
+    e2e_file = None
+    if not args.headline_only and key in ("native", "synth1b"):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import e2e_file_bench
+            e2e_file = e2e_file_bench.measure(gpus=n_gpus, reps=2, ref_sample=300_000)
+        except BaseException as e:  # SystemExit from a failed child included: report, keep the line
+            e2e_file = {"error": str(e)[:500]}
     line = {
         "metric": "options_priced_per_sec", "value": head["value"], "unit": "options/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": scaling,
@@ -647,6 +683,10 @@ def ours(args):
     line.update(extra)
     if inproc is not None:
         line["inproc"] = inproc
+    if other is not None:
+        line["other_configs"] = other
+    if e2e_file is not None:
+        line["e2e_file"] = e2e_file
     print(json.dumps(line), flush=True)
     return 0
 

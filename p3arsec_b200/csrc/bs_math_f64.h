@@ -129,15 +129,28 @@ BS_HD double exp_f64(double x, const double *tab)
     return x < -708.0 ? 0.0 : from_bits(scaled);
 }
 
+// Where log_f64 reads its table pair {1/c_i, log c_i} from.  PlainLogTab: the block filled by fill_tables.  Kernels whose
+// lanes look up unrelated intervals at the same time may pass a bank-replicated copy instead (sw_kernels.cuh).
+struct PlainLogTab {
+    const double *tab;
+    BS_HD void pair(int i, double &rc, double &lc) const
+    {
+        rc = tab[TAB_LOG + 2 * i];
+        lc = tab[TAB_LOG + 2 * i + 1];
+    }
+};
+
 // log(x) for normal x > 0.  Absolute error ~1e-16 (relative to max(1, |log x|)); arguments close to 1 keep a small
 // relative error because the table entry of their interval is already reduced by ln 2 (LOG_SPLIT).
-BS_HD double log_f64(double x, const double *tab)
+template <class LT>
+BS_HD double log_f64_t(double x, const LT &lt)
 {
     const uint64_t b = to_bits(x);
     const int i = (int)(b >> 46) & 63;            // top 6 mantissa bits: m in [1 + i/64, 1 + (i+1)/64)
     const int e = (int)(b >> 52) - 1023 + (i >= LOG_SPLIT ? 1 : 0);
     const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
-    const double rc = tab[TAB_LOG + 2 * i], lc = tab[TAB_LOG + 2 * i + 1];
+    double rc, lc;
+    lt.pair(i, rc, lc);
     const double r = fma(m, rc, -1.0);            // |r| < 2^-7: r^8/8 < 2e-18
     double q = fma(kd(K_LOG_C7), r, kd(K_LOG_C6));  // r - r^2/2 + r^3/3 - ... + r^7/7
     q = fma(q, r, kd(K_LOG_C5));
@@ -147,6 +160,11 @@ BS_HD double log_f64(double x, const double *tab)
     const double lp = fma(r * r, q, r);           // log1p(r)
     const double ed = (double)e;
     return fma(ed, kd(K_LN2_HI), lc + fma(ed, kd(K_LN2_LO), lp));
+}
+BS_HD double log_f64(double x, const double *tab)
+{
+    const PlainLogTab lt = {tab};
+    return log_f64_t(x, lt);
 }
 
 // exp(x) without exp_f64's underflow guard, for callers that have range-checked x themselves (|x| < 700); the

@@ -183,6 +183,25 @@ struct ExpTab {
     SW_HD double at(int j) const { return t[(j << REP_SHIFT) + lane]; }
 };
 constexpr int EXP_REP_SHIFT = 4, EXP_REP_DOUBLES = 64 << EXP_REP_SHIFT;
+// The same for log_f64's {1/c, log c} pairs, read as one 128-bit load: a quarter-warp (8 lanes) per wavefront, so 8 copies
+// interleaved [i][lane & 7] are conflict-free (8 KB per CTA).
+template <int REP_SHIFT>
+struct LogTabRep {
+    const double *t;
+    int lane;
+    SW_HD void pair(int i, double &rc, double &lc) const
+    {
+#if defined(__CUDA_ARCH__)
+        const double2 v = reinterpret_cast<const double2 *>(t)[(i << REP_SHIFT) + lane];
+        rc = v.x;
+        lc = v.y;
+#else
+        rc = t[2 * ((i << REP_SHIFT) + lane)];
+        lc = t[2 * ((i << REP_SHIFT) + lane) + 1];
+#endif
+    }
+};
+constexpr int LOG_REP_SHIFT = 3, LOG_REP_DOUBLES = (64 << LOG_REP_SHIFT) * 2;
 template <class ET>
 SW_HD double exp_core(double x, const ET &et)
 {
@@ -220,7 +239,13 @@ constexpr uint32_t S_LO = 171798692u, S_HI = 1975684955u;
 // CumNormalInv's tail branch for draw k of the trial whose first residue is x0, branch-free so that several of them can
 // be interleaved: z = -/+ P8(log(-log(min(u, 1 - u)))).  A draw of exactly 0 (counter a multiple of 2^31 - 1) gives
 // log(-log(0)) = +inf in the reference, hence z = -inf.
-SW_HD double tail_normal(uint32_t x0, int k, const double *tab, const double *tailtab)
+// TWO_LOGS: P8(log(-log r)) as the reference writes it -- two logarithms and Moro's own coefficients (uniform operands),
+// 20 FP64 operations and two table loads; otherwise one logarithm + the composite table of sw_tail.h, 9 FP64 operations and
+// ten per-lane table loads after the logarithm's one.  The full-work kernel is bound by instruction issue and, with the
+// composite table, by shared-memory bank conflicts of those per-lane loads (30 % of all wavefronts, profiles/
+// r01_sw_ncu_one_full.txt); see SW_FULL_TWO_LOGS.
+template <bool TWO_LOGS, class LT>
+SW_HD double tail_normal(uint32_t x0, int k, const LT &lt, const double *tailtab)
 {
     uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
     xk = xk >= RU_M ? xk - RU_M : xk;
@@ -228,19 +253,20 @@ SW_HD double tail_normal(uint32_t x0, int k, const double *tab, const double *ta
     const double u = (double)(int)s * 4.656612875e-10;
     const bool upper = s > S_HI;
     const double r = upper ? 1.0 - u : u;
-#if defined(SW_TAIL_TWO_LOGS)
-    const double w = bsm::log_f64(-bsm::log_f64(r, tab), tab);
-    double p = fma(w, MORO_C[8], MORO_C[7]);
-    p = fma(w, p, MORO_C[6]);
-    p = fma(w, p, MORO_C[5]);
-    p = fma(w, p, MORO_C[4]);
-    p = fma(w, p, MORO_C[3]);
-    p = fma(w, p, MORO_C[2]);
-    p = fma(w, p, MORO_C[1]);
-    p = fma(w, p, MORO_C[0]);
-#else
-    double p = swt::moro_tail(r, tab, tailtab);  // P8(log(-log r)): one logarithm + the composite table (sw_tail.h)
-#endif
+    double p;
+    if (TWO_LOGS) {
+        const double w = bsm::log_f64_t(-bsm::log_f64_t(r, lt), lt);
+        p = fma(w, MORO_C[8], MORO_C[7]);
+        p = fma(w, p, MORO_C[6]);
+        p = fma(w, p, MORO_C[5]);
+        p = fma(w, p, MORO_C[4]);
+        p = fma(w, p, MORO_C[3]);
+        p = fma(w, p, MORO_C[2]);
+        p = fma(w, p, MORO_C[1]);
+        p = fma(w, p, MORO_C[0]);
+    } else {
+        p = swt::moro_tail_t(r, lt, tailtab);  // P8(log(-log r)): one logarithm + the composite table (sw_tail.h)
+    }
     p = s == 0 ? INFINITY : p;
     return upper ? p : -p;
 }
@@ -263,6 +289,12 @@ SW_HD void load_tables(double *__restrict__ smem_tail_then_tab, const double *__
 SW_HD void load_exp_replicated(double *__restrict__ xexp, const double *__restrict__ g, int tid)
 {
     for (int i = tid; i < EXP_REP_DOUBLES; i += THREADS) xexp[i] = g[swt::TAIL_DOUBLES + bsm::TAB_EXP + (i >> EXP_REP_SHIFT)];
+}
+SW_HD void load_log_replicated(double *__restrict__ xlog, const double *__restrict__ g, int tid)
+{
+    // element e = 2 * ((i << LOG_REP_SHIFT) + lane) + c  <-  table pair i, component c
+    for (int e = tid; e < LOG_REP_DOUBLES; e += THREADS)
+        xlog[e] = g[swt::TAIL_DOUBLES + bsm::TAB_LOG + 2 * (e >> (LOG_REP_SHIFT + 1)) + (e & 1)];
 }
 
 // Block-wide sum of two doubles; result valid in thread 0.
@@ -342,6 +374,7 @@ struct FastShared {
     double pay[FN];
     double red[2][THREADS / 32];
     double xexp[EXP_REP_DOUBLES];  // 2^(j/64) replicated [j][lane & 15]: conflict-free whatever the lanes' j (ExpTab)
+    double xlog[LOG_REP_DOUBLES];  // {1/c, log c} replicated [i][lane & 7] (LogTabRep)
 };
 // Behind FastShared in dynamic shared memory: z[z_rows][THREADS], the trial's normals [draw][thread] (conflict-free) --
 // all 30 draws for the full kernel, 3 x (largest swap start index of the launch) for the lean one.
@@ -367,10 +400,14 @@ SW_HOST_DEVICE constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(Fa
 #endif
 constexpr int TAIL_TRIP = SW_TAIL_TRIP;
 
-template <bool LEAN>
-SW_HD void normals(const double *__restrict__ tab, const double *__restrict__ tailtab, double *__restrict__ z, int tid, uint32_t x0,
+#ifndef SW_FULL_TWO_LOGS
+#define SW_FULL_TWO_LOGS 1  /* full-work kernels: Moro's tail with two logarithms (no per-lane composite-table loads) */
+#endif
+template <bool LEAN, class LT>
+SW_HD void normals(const LT &tab, const double *__restrict__ tailtab, double *__restrict__ z, int tid, uint32_t x0,
                                         int steps)
 {
+    constexpr bool TWO_LOGS = !LEAN && SW_FULL_TWO_LOGS;
     constexpr int G = LEAN ? FF : SW_PHASE_A_GROUP;
     uint32_t tail = 0;
 #pragma unroll
@@ -426,7 +463,7 @@ SW_HD void normals(const double *__restrict__ tab, const double *__restrict__ ta
         const int k0 = ffs32(tail) - 1;
         tail &= tail - 1;
         if (LEAN) {  // three or six draws per trial: rarely more than one tail draw per lane (two per trip measured 8 % slower)
-            z[k0 * THREADS + tid] = tail_normal(x0, k0, tab, tailtab);
+            z[k0 * THREADS + tid] = tail_normal<TWO_LOGS>(x0, k0, tab, tailtab);
         } else {
             // TRIP draws per trip with interleaved chains; with fewer left the last trip repeats draw k0
             int kk[TAIL_TRIP];
@@ -438,7 +475,7 @@ SW_HD void normals(const double *__restrict__ tab, const double *__restrict__ ta
                 tail &= tail - 1;  // (0 & anything == 0)
             }
 #pragma unroll
-            for (int i = 0; i < TAIL_TRIP; ++i) zz[i] = tail_normal(x0, kk[i], tab, tailtab);
+            for (int i = 0; i < TAIL_TRIP; ++i) zz[i] = tail_normal<TWO_LOGS>(x0, kk[i], tab, tailtab);
 #pragma unroll
             for (int i = 0; i < TAIL_TRIP; ++i) z[kk[i] * THREADS + tid] = zz[i];
         }
@@ -526,7 +563,9 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
     static_assert(offsetof(FastShared, tail) == 0 && offsetof(FastShared, tab) == sizeof(double) * swt::TAIL_DOUBLES, "[tail | tab] first");
     load_tables(sh.tail, tables, tid);
     load_exp_replicated(sh.xexp, tables, tid);
+    load_log_replicated(sh.xlog, tables, tid);
     const ExpTab<EXP_REP_SHIFT> et = {sh.xexp, tid & ((1 << EXP_REP_SHIFT) - 1)};
+    const LogTabRep<LOG_REP_SHIFT> lt = {sh.xlog, tid & ((1 << LOG_REP_SHIFT) - 1)};
 
     int cur = -1;
     double ddelt = 0, swap_ddelt = 0;
@@ -567,7 +606,7 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             if (t >= sims) break;
 
             // ---- phase A + tail pass: the trial's normals into sh.z (see normals())
-            normals<LEAN>(sh.tab, sh.tail, z, tid, ru_residue(seed + t * FD), steps);
+            normals<LEAN>(lt, sh.tail, z, tid, ru_residue(seed + t * FD), steps);
 
             // ---- phase B: path, discount factors, payoff; specialised on the swap start index (1..3 covers every
             // swaption the reference drivers create: dMaturity = 1, dYears in [5, 20))
@@ -612,6 +651,7 @@ struct OneShared {
     double tab[bsm::TAB_DOUBLES];
     double red[2][THREADS / 32];
     double xexp[EXP_REP_DOUBLES];  // 2^(j/64) replicated [j][lane & 15] (ExpTab)
+    double xlog[LOG_REP_DOUBLES];  // {1/c, log c} replicated [i][lane & 7] (LogTabRep)
 };
 static_assert(sizeof(OneShared) % 16 == 0, "z starts 16-byte aligned");
 SW_HOST_DEVICE constexpr size_t one_shared_bytes(int z_rows) { return sizeof(OneShared) + (size_t)z_rows * THREADS * sizeof(double); }
@@ -629,7 +669,9 @@ sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ p
     static_assert(offsetof(OneShared, tail) == 0 && offsetof(OneShared, tab) == sizeof(double) * swt::TAIL_DOUBLES, "[tail | tab] first");
     load_tables(sh.tail, tables, tid);
     load_exp_replicated(sh.xexp, tables, tid);
+    load_log_replicated(sh.xlog, tables, tid);
     const ExpTab<EXP_REP_SHIFT> et = {sh.xexp, tid & ((1 << EXP_REP_SHIFT) - 1)};
+    const LogTabRep<LOG_REP_SHIFT> lt = {sh.xlog, tid & ((1 << LOG_REP_SHIFT) - 1)};
     const int steps = LEAN ? P.start : FN - 1;
     const int swap_end = LEAN ? P.last_pay : P.len - 1;
 
@@ -639,7 +681,7 @@ sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ p
         for (int m = 0; m < P.tpt; ++m) {
             const long long t = (long long)chunk * P.chunk_trials + (long long)m * THREADS + tid;
             if (t >= P.sims) break;
-            normals<LEAN>(sh.tab, sh.tail, z, tid, ru_residue(P.seed + t * FD), steps);
+            normals<LEAN>(lt, sh.tail, z, tid, ru_residue(P.seed + t * FD), steps);
             uint32_t worst = 0;
             double disc;
             switch (P.start) {

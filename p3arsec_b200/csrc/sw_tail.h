@@ -31,10 +31,12 @@ BS_HD void fill_tail(double *t, int first, int step)
     }
 }
 
-// logtab: the block filled by bsm::fill_tables; tt: the block filled by fill_tail (16-byte aligned).
-BS_HD double moro_tail(double r, const double *logtab, const double *tt)
+// lt: where log_f64_t finds its table (bsm::PlainLogTab or a bank-replicated copy); tt: the block filled by fill_tail
+// (16-byte aligned).
+template <class LT>
+BS_HD double moro_tail_t(double r, const LT &lt, const double *tt)
 {
-    const double y = -bsm::log_f64(r, logtab);                          // in [2.52, 21.5]
+    const double y = -bsm::log_f64_t(r, lt);                            // in [2.52, 21.5]
     const int idx = ((int)(bsm::to_bits(y) >> 48) - 0x4000) & 63;       // 16 (exponent - 1) + top four mantissa bits
 #if SW_TAIL_LAYOUT == 0
     const double *a = tt + idx * TAIL_COLS;
@@ -53,6 +55,11 @@ BS_HD double moro_tail(double r, const double *logtab, const double *tt)
     p = fma(p, d, SW_A(2));
     return fma(p, d, SW_A(1));
 #undef SW_A
+}
+BS_HD double moro_tail(double r, const double *logtab, const double *tt)
+{
+    const bsm::PlainLogTab lt = {logtab};
+    return moro_tail_t(r, lt, tt);
 }
 
 }  // namespace swt

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -159,3 +160,16 @@ def test_integration_patches_apply_to_the_reference(tmp_path):
     subprocess.run(["patch", "-s", "-o", step2, step1, os.path.join(integ, "blackscholes.c.caf_cuda.patch")], check=True)
     text = open(step2).read()
     assert "bs_gpu_price_aos(gpu, data_vec.data(), nv, res.data(), 1)" in text and "bs_gpu_price(gpu, NUM_RUNS" in text
+
+
+def test_limit_devices_edits_cuda_visible_devices():
+    # bs_gpu_limit_devices only rewrites the environment (it must run before the first CUDA call); checked in a child process
+    code = ("import os, ctypes; L = ctypes.CDLL(%r); "
+            "os.environ.pop('CUDA_VISIBLE_DEVICES', None); assert L.bs_gpu_limit_devices(3) == 0; a = os.environ.get('CUDA_VISIBLE_DEVICES'); "
+            "import ctypes.util; libc = ctypes.CDLL(None); libc.getenv.restype = ctypes.c_char_p; a = libc.getenv(b'CUDA_VISIBLE_DEVICES'); "
+            "libc.setenv(b'CUDA_VISIBLE_DEVICES', b'GPU-aa,5,2,7', 1); assert L.bs_gpu_limit_devices(2) == 0; b = libc.getenv(b'CUDA_VISIBLE_DEVICES'); "
+            "assert L.bs_gpu_limit_devices(9) == 0; c = libc.getenv(b'CUDA_VISIBLE_DEVICES'); assert L.bs_gpu_limit_devices(0) == -1; "
+            "print(a.decode(), b.decode(), c.decode())") % host.LIB_PATH
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["0,1,2", "GPU-aa,5", "GPU-aa,5"]

@@ -31,11 +31,16 @@ def main():
     ap.add_argument("--n", type=int, default=250_000_000)
     ap.add_argument("--runs", type=int, default=1000)
     ap.add_argument("--rois", type=int, default=4)
+    ap.add_argument("--fp", type=int, default=4)
     a = ap.parse_args()
     cases = [("fast", dict(math=host.MATH_FAST)), ("probe", dict(variant=2)), ("ieee", dict(math=host.MATH_IEEE)),
              ("fast u2", dict(math=host.MATH_FAST, unroll=2, blocks_per_sm=0, threads_per_block=256))]
+    if a.fp == 8:  # fp64: the TMA ring kernel (default), software-pipelined LDG, plain LDG, and the two traffic probes
+        cases = [("tma", dict(variant=4)), ("ldg+pipe", dict(variant=1)), ("ldg", dict(variant=0, threads_per_block=256)),
+                 ("probe tma", dict(variant=6)), ("probe ldg", dict(variant=2)), ("tma", dict(variant=4))]
+    bpo = host.bytes_per_option(a.fp)
     for name, kw in cases:
-        with host.BlackScholesGPU(a.n, fp_bytes=4, host_staging=False, with_dgrefval=False, **kw) as bs:
+        with host.BlackScholesGPU(a.n, fp_bytes=a.fp, host_staging=False, with_dgrefval=False, **kw) as bs:
             bs.fill_synthetic(0)
             bs.run(10)
             for i in range(a.rois):
@@ -51,7 +56,7 @@ def main():
                 for r in smp.rows:
                     reasons |= r[2]
                 print("%-8s ROI %d: %8.1f ms  %7.1f GB/s  %7.2f Gopt/s | SM MHz med %d min %d  mem MHz %d  power max %.0f W avg %.0f W  reasons 0x%x" % (
-                    name, i, ms, 28.0 * a.n * a.runs / ms / 1e6, a.n * a.runs / ms / 1e6, sm[len(sm) // 2], sm[0], smp.rows[-1][3], max(pw),
+                    name, i, ms, bpo * a.n * a.runs / ms / 1e6, a.n * a.runs / ms / 1e6, sm[len(sm) // 2], sm[0], smp.rows[-1][3], max(pw),
                     sum(pw) / len(pw), reasons), flush=True)
         time.sleep(2.0)
 

@@ -21,7 +21,8 @@ static double one_trial(const SRC &src, const double *tab, const double *tail, d
     const int tid = (int)(t % THREADS);  // any lane: exercises the [draw][thread] indexing of z
     const int steps = LEAN ? P.start : FN - 1;
     const int swap_end = LEAN ? P.last_pay : P.len - 1;
-    normals<LEAN>(tab, tail, z, tid, ru_residue(P.seed + t * FD), steps);
+    const bsm::PlainLogTab plt = {tab};
+    normals<LEAN>(plt, tail, z, tid, ru_residue(P.seed + t * FD), steps);
     const ExpTab<0> et = {tab + bsm::TAB_EXP, 0};  // the plain table: bank layout is a device-only concern
     uint32_t worst = 0;
     double disc;
