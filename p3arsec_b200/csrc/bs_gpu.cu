@@ -100,7 +100,7 @@ struct bs_gpu_ctx {
     unsigned flags = 0;
     int math = BS_MATH_FAST;
     int cfg_threads = 0, cfg_blocks_per_sm = 0, unroll = 0, variant = 0;
-    bool tma_wide = false;  // fp64 TMA kernel: 24 consumer warps / 3 stages instead of 16 / 4
+    int tma_shape = 0;  // fp64 TMA kernel: 0 = 16 consumer warps / 4 stages; 1 = 24 / 3; 2 = 16 warps, two groups per thread, 2 stages
     std::vector<Shard> shards;
     void *host[BS_BUF_COUNT] = {nullptr};  // page-aligned anonymous mappings, pinned lazily by the device threads
     size_t host_bytes[BS_BUF_COUNT] = {0};
@@ -211,17 +211,17 @@ template <typename FP, int SHAPE> const void *tma_kernel(int math)
 const void *tma_kernel_ptr(const bs_gpu_ctx *c)
 {
     if (c->fp_bytes == 4) return tma_kernel<float, 0>(kernel_math(c));
-    return c->tma_wide ? tma_kernel<double, 1>(kernel_math(c)) : tma_kernel<double, 0>(kernel_math(c));
+    return c->tma_shape == 2 ? tma_kernel<double, 2>(kernel_math(c)) : c->tma_shape == 1 ? tma_kernel<double, 1>(kernel_math(c)) : tma_kernel<double, 0>(kernel_math(c));
 }
 size_t tma_smem(const bs_gpu_ctx *c)
 {
     if (c->fp_bytes == 4) return bsk::tma_smem_bytes<float, 0>();
-    return c->tma_wide ? bsk::tma_smem_bytes<double, 1>() : bsk::tma_smem_bytes<double, 0>();
+    return c->tma_shape == 2 ? bsk::tma_smem_bytes<double, 2>() : c->tma_shape == 1 ? bsk::tma_smem_bytes<double, 1>() : bsk::tma_smem_bytes<double, 0>();
 }
 int tma_threads(const bs_gpu_ctx *c)
 {
     if (c->fp_bytes == 4) return bsk::tma_threads<float, 0>();
-    return c->tma_wide ? bsk::tma_threads<double, 1>() : bsk::tma_threads<double, 0>();
+    return c->tma_shape == 2 ? bsk::tma_threads<double, 2>() : c->tma_shape == 1 ? bsk::tma_threads<double, 1>() : bsk::tma_threads<double, 0>();
 }
 KernelF32 pick_f32(const bs_gpu_ctx *c, bool chk) { return pick_kernel<float>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
 KernelF64 pick_f64(const bs_gpu_ctx *c, bool chk) { return pick_kernel<double>(kernel_math(c), c->unroll, chk, (c->variant & VARIANT_PIPE) != 0); }
@@ -1098,8 +1098,8 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST && !sustained) c->cfg_blocks_per_sm = 4;
     c->variant = cfg->variant;
     {
-        const char *w = getenv("BS_GPU_TMA_WIDE");  // measurement knob for the fp64 TMA kernel's shape
-        c->tma_wide = c->fp_bytes == 8 && w && *w == '1';
+        const char *w = getenv("BS_GPU_TMA_WIDE");  // measurement knob for the fp64 TMA kernel's shape (0, 1, 2)
+        c->tma_shape = (c->fp_bytes == 8 && w && (*w == '1' || *w == '2')) ? *w - '0' : 0;
     }
     // fp64 (unless the caller chose a geometry/variant explicitly): the fast-math kernel takes its inputs through the
     // bulk-copy ring (bs_map_tma: 81.0 us per 10M options = 6.42 TB/s against 85.9 us with software-pipelined LDG.128

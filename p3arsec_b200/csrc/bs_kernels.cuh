@@ -549,6 +549,10 @@ template <typename FP, int SHAPE> struct TmaCfg;
 template <int SHAPE> struct TmaCfg<float, SHAPE> { enum { TILE = 2048, STAGES = 4, CONSUMERS = 512 }; };  // 6 x 8 KB per stage; 192 KB per CTA, 1 CTA per SM
 template <> struct TmaCfg<double, 0> { enum { TILE = 1024, STAGES = 4, CONSUMERS = 512 }; };              // 5 x 8 KB + 4 KB per stage; 176 KB per CTA
 template <> struct TmaCfg<double, 1> { enum { TILE = 1536, STAGES = 3, CONSUMERS = 768 }; };              // 66 KB per stage; 198 KB per CTA
+// SHAPE 2 (fp64): two groups (four options) per consumer thread and tile -- twice the independent work per warp for the
+// dependent DFMA chains, and the per-tile overhead (barrier wait, addresses, loop) paid once per four options; the same
+// 176 KB in flight as two stages of 88 KB.
+template <> struct TmaCfg<double, 2> { enum { TILE = 2048, STAGES = 2, CONSUMERS = 512 }; };
 
 template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_stage_bytes() { return (size_t)TmaCfg<FP, SHAPE>::TILE * (5 * sizeof(FP) + sizeof(int)); }
 template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_smem_bytes()
@@ -614,22 +618,31 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
             const int st = it % STAGES;
             mbar_wait(&full[st], (it / STAGES) & 1);
             const unsigned char *src = stage_base + (size_t)st * STAGE_BYTES;
-            // GROUPS groups per tile, 256 consumers: fp32 exactly one group each (1024/4), fp64 too (512/2)
-            static_assert(GROUPS == TMA_CONSUMERS, "one group per consumer thread and tile");
-            const int gi = threadIdx.x;
-            const vec vs = reinterpret_cast<const vec *>(src + 0 * FP_TILE_BYTES)[gi];
-            const vec vk = reinterpret_cast<const vec *>(src + 1 * FP_TILE_BYTES)[gi];
-            const vec vr = reinterpret_cast<const vec *>(src + 2 * FP_TILE_BYTES)[gi];
-            const vec vv = reinterpret_cast<const vec *>(src + 3 * FP_TILE_BYTES)[gi];
-            const vec vt = reinterpret_cast<const vec *>(src + 4 * FP_TILE_BYTES)[gi];
-            const ivec vo = reinterpret_cast<const ivec *>(src + 5 * FP_TILE_BYTES)[gi];
+            // GROUPS groups per tile, GPT of them per consumer thread (one, or two for shape 2): thread i owns groups i, i + CONSUMERS
+            enum { GPT = GROUPS / TMA_CONSUMERS };
+            static_assert(GROUPS == GPT * TMA_CONSUMERS, "whole groups per consumer thread and tile");
+            vec vs[GPT], vk[GPT], vr[GPT], vv[GPT], vt[GPT];
+            ivec vo[GPT];
+#pragma unroll
+            for (int u = 0; u < GPT; u++) {
+                const int gi = threadIdx.x + u * TMA_CONSUMERS;
+                vs[u] = reinterpret_cast<const vec *>(src + 0 * FP_TILE_BYTES)[gi];
+                vk[u] = reinterpret_cast<const vec *>(src + 1 * FP_TILE_BYTES)[gi];
+                vr[u] = reinterpret_cast<const vec *>(src + 2 * FP_TILE_BYTES)[gi];
+                vv[u] = reinterpret_cast<const vec *>(src + 3 * FP_TILE_BYTES)[gi];
+                vt[u] = reinterpret_cast<const vec *>(src + 4 * FP_TILE_BYTES)[gi];
+                vo[u] = reinterpret_cast<const ivec *>(src + 5 * FP_TILE_BYTES)[gi];
+            }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);   // stage is free again: refill overlaps our math
-            vec p;
 #pragma unroll
-            for (int l = 0; l < LANES; l++)
-                set_lane(p, l, price_any<MATH>(lane(vs, l), lane(vk, l), lane(vr, l), lane(vv, l), lane(vt, l), lane(vo, l), s_tab));
-            st_stream(p_out + t * GROUPS + gi, p);
+            for (int u = 0; u < GPT; u++) {
+                vec p;
+#pragma unroll
+                for (int l = 0; l < LANES; l++)
+                    set_lane(p, l, price_any<MATH>(lane(vs[u], l), lane(vk[u], l), lane(vr[u], l), lane(vv[u], l), lane(vt[u], l), lane(vo[u], l), s_tab));
+                st_stream(p_out + t * GROUPS + threadIdx.x + u * TMA_CONSUMERS, p);
+            }
         }
         // the last n % TILE options (no whole tile): plain loads, block 0 only
         if (blockIdx.x == 0) {

@@ -53,6 +53,17 @@ BS_HD uint64_t to_bits(double d)
 #endif
 }
 
+// m * 2^k for a normal m and a normal result, as an integer add on the high word only (one IADD on the device; the
+// 64-bit form costs an add with carry on a register pair).
+BS_HD double scale_by_pow2(double m, int k)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(m) + (k << 20), __double2loint(m));
+#else
+    return from_bits(to_bits(m) + ((uint64_t)(int64_t)k << 52));
+#endif
+}
+
 // Scalar constant i of bs_tables_f64.h (a __constant__ bank operand / LDCU on the device).
 BS_HD double kd(int i) { return from_bits(KD_BITS[i]); }
 
@@ -182,9 +193,7 @@ BS_HD double exp_core_f64(double x, const double *tab)
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
     const double T = tab[TAB_EXP + (n & 63)];
-    const uint64_t mb = to_bits(fma(T, em1, T));  // in [0.99, 2.0)
-    const uint32_t hi = (uint32_t)(mb >> 32) + ((uint32_t)(n >> 6) << 20);
-    return from_bits(((uint64_t)hi << 32) | (mb & 0xffffffffull));
+    return scale_by_pow2(fma(T, em1, T), n >> 6);  // the mantissa product is in [0.99, 2.0)
 }
 
 // poly(k) with k = 1/(1 + 0.2316419|d|): the CNDF tail 1 - N(|d|) is exp(-d^2/2) k poly(k) / sqrt(2 pi); the constants

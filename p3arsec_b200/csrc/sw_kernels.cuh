@@ -217,8 +217,7 @@ SW_HD double exp_core(double x, const ET &et)
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
     const double T = et.at(n & 63);
-    const double m = fma(T, em1, T);
-    return from_bits(to_bits(m) + ((uint64_t)(int64_t)(n >> 6) << 52));
+    return scale_by_pow2(fma(T, em1, T), n >> 6);
 }
 // |x| >= 700, inf or NaN <=> (high word of x, sign cleared) >= EXP_HI_LIMIT.  The fast kernel evaluates every
 // exponential with exp_core, branch-free, and only tracks the largest such high word of the trial (LOP3 + VIMNMX on the
@@ -400,8 +399,13 @@ SW_HOST_DEVICE constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(Fa
 #endif
 constexpr int TAIL_TRIP = SW_TAIL_TRIP;
 
+// Measured on B200, PARSEC native (profiles/r02_sw_tail_variants.txt): composite table 12.62 G trials/s with 30 % of the
+// shared-memory wavefronts being bank conflicts (the ten per-lane coefficient loads of each tail: lanes hold unrelated
+// rows); two logarithms 12.12 G trials/s with 0.09 % conflicts (+60 FP64 instructions per trial, longer dependent
+// chains: `wait` stalls 1.09 -> 1.52 per issue).  Throughput is the metric, so the composite table stays the default; the
+// exp and log tables, which could be replicated per lane in 16 KB, are conflict-free in both.
 #ifndef SW_FULL_TWO_LOGS
-#define SW_FULL_TWO_LOGS 1  /* full-work kernels: Moro's tail with two logarithms (no per-lane composite-table loads) */
+#define SW_FULL_TWO_LOGS 0  /* 1: full-work kernels evaluate Moro's tail with two logarithms (no composite-table loads) */
 #endif
 template <bool LEAN, class LT>
 SW_HD void normals(const LT &tab, const double *__restrict__ tailtab, double *__restrict__ z, int tid, uint32_t x0,

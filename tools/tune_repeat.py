@@ -28,6 +28,8 @@ CONFIGS = {
     "fp64r2": [(8, "fast", 1, 256, 0, 1), (8, "fast", 1, 224, 0, 1), (8, "fast", 1, 192, 0, 1), (8, "fast", 1, 160, 0, 1), (8, "fast", 1, 128, 0, 1),
                (8, "fast", 1, 96, 0, 1), (8, "fast", 1, 64, 0, 1), (8, "fast", 1, 256, 0, 0), (8, "fast", 1, 192, 0, 0), (8, "fast", 1, 128, 0, 0),
                (8, "fast", 2, 128, 0, 0), (8, "fast", 2, 128, 0, 1), (8, "fast", 2, 256, 0, 1), (8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2)],
+    "fp64tma2": [(8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 68), (8, "fast", 1, 256, 0, 36), (8, "fast", 1, 256, 0, 1), (8, "fast", 1, 256, 0, 6),
+                 (8, "fast", 1, 256, 0, 70), (8, "fast", 1, 256, 0, 2)],
     "fp64tma": [(8, "fast", 1, 256, 0, 1), (8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 36), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2),
                 (8, "fast", 1, 256, 0, 6), (8, "fast", 1, 256, 0, 38), (8, "ieee", 1, 256, 0, 4), (8, "ieee", 1, 256, 0, 36), (8, "ieee", 1, 256, 0, 1)],
     "fp64": [(8, "fast", 1, 256, 0, 0), (8, "fast", 2, 256, 0, 0), (8, "fast", 1, 256, 0, 1), (8, "fast", 1, 128, 0, 1), (8, "fast", 2, 128, 0, 1),
@@ -45,7 +47,7 @@ def main():
     a = ap.parse_args()
     ctxs = []
     for fp, m, u, t, b, var in CONFIGS[a.which]:
-        os.environ["BS_GPU_TMA_WIDE"] = "1" if var & 32 else "0"   # read by bs_gpu_init_ex: shape of the fp64 TMA kernel
+        os.environ["BS_GPU_TMA_WIDE"] = "2" if var & 64 else "1" if var & 32 else "0"   # read by bs_gpu_init_ex: shape of the fp64 TMA kernel
         bs = host.BlackScholesGPU(a.n, fp_bytes=fp, host_staging=False, with_dgrefval=False, math=M[m], unroll=u,
                                   threads_per_block=t, blocks_per_sm=b, variant=var & 7, pdl=bool(var & 16))
         bs.fill_synthetic(0)
@@ -58,7 +60,7 @@ def main():
     print("%-4s %-11s %6s %7s %6s %7s | %9s %9s | %9s %9s" % ("fp", "math", "unroll", "threads", "blk/SM", "blocks", "med us", "min us", "med GB/s", "Gopt/s"))
     for (fp, m, u, t, b, var), bs, times in sorted(ctxs, key=lambda c: statistics.median(c[2])):
         med, mn = statistics.median(times), min(times)
-        m = ("PROBE" if var & 2 else m + ("+p" if var & 1 else "")) + ("/tma" if var & 4 else "") + ("w" if var & 32 else "") + ("/pdl" if var & 16 else "")
+        m = ("PROBE" if var & 2 else m + ("+p" if var & 1 else "")) + ("/tma" if var & 4 else "") + ("w" if var & 32 else "") + ("x2" if var & 64 else "") + ("/pdl" if var & 16 else "")
         print("%-4d %-11s %6d %7d %6d %7d | %9.2f %9.2f | %9.1f %9.2f" % (fp * 8, m, u, t, b, bs.launch()["blocks"], med, mn,
               host.bytes_per_option(fp) * a.n / med / 1e3, a.n / med / 1e3))
         bs.close()
