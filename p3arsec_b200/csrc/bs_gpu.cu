@@ -1097,6 +1097,11 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     c->unroll = cfg->unroll ? cfg->unroll : (sustained ? 2 : 1);
     if (!c->cfg_blocks_per_sm && !c->cfg_threads && c->fp_bytes == 4 && c->math == BS_MATH_FAST && !sustained) c->cfg_blocks_per_sm = 4;
     c->variant = cfg->variant;
+    // Sets that a launch finishes in a microsecond or two (simsmall: 4,096 options) are bound by the gap between the runs'
+    // launches, not by anything the kernel does: programmatic dependent launch lets run j+1 be scheduled while run j
+    // drains (measured on B200, tools/simsmall_pdl.py -> profiles/r02_simsmall_pdl.txt: 1.64 -> 1.43 us per run at 4K
+    // options, 1.98 -> 1.69 at 64K; from 256K options on it costs time, as it does for the large sets).
+    if (c->n / (size_t)cfg->num_gpus <= ((size_t)128 << 10) && !cfg->variant) c->flags |= BS_GPU_FLAG_PDL;
     {
         const char *w = getenv("BS_GPU_TMA_WIDE");  // measurement knob for the fp64 TMA kernel's shape (0, 1, 2)
         c->tma_shape = (c->fp_bytes == 8 && w && (*w == '1' || *w == '2')) ? *w - '0' : 0;
@@ -1443,8 +1448,9 @@ int bs_gpu_get_launch(bs_gpu_ctx *c, int *math, int *threads_per_block, int *blo
     if (ready != BS_GPU_OK) return ready;
     if (c->shards.empty()) return BS_GPU_ERR_STATE;
     if (math) *math = c->math;
-    if (threads_per_block) *threads_per_block = c->shards[0].threads;
-    if (blocks) *blocks = c->shards[0].blocks;
+    const bool tma = use_tma(c, false);  // the geometry of the kernel that plain (non-ERR_CHK) runs launch
+    if (threads_per_block) *threads_per_block = tma ? tma_threads(c) : c->shards[0].threads;
+    if (blocks) *blocks = tma ? c->shards[0].tma_blocks : c->shards[0].blocks;
     return BS_GPU_OK;
 }
 
