@@ -650,6 +650,17 @@ def ours(args):
     ranks.close()
     if rank != 0:
         return 0
+    if other is not None:
+        # the sibling Map, measured by its own tool with the same contract: a child process, after
+        # this process has closed its contexts, so that its line is part of this driver-run record too
+        try:
+            cp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sw_bench.py"), "--workload", "native", "--steps", str(max(3, min(args.steps, 10))),
+                                 "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+            sw = json.loads([l for l in cp.stdout.splitlines() if l.startswith("{")][-1])
+            other["swaptions_native"] = {k: sw.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "dtype", "config", "e2e", "roofline",
+                                                                 "gpu_launches", "parity_spot_max_rel", "clocks")}
+        except Exception as e:
+            other["swaptions_native"] = {"error": str(e)[:300]}
     inproc = None
     if world > 1 and not args.headline_only:
         time.sleep(2.0)  # the other ranks are exiting: let their contexts go before GPUs 1..N-1 are used from here
