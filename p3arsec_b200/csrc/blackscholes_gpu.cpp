@@ -150,6 +150,17 @@ int main(int argc, char **argv)
     if (wantGpus > have) wantGpus = have;
     cfg.num_gpus = wantGpus;
     cfg.flags = BS_GPU_FLAG_WITH_DGREFVAL;
+    // BS_GPU_MATH=fast|ieee|reference selects the math mode (include/bs_gpu.h); with "reference" the prices file is byte for
+    // byte the one the reference's fp32 CPU build writes (its double-literal promotions and glibc's expf/logf reproduced)
+    if (const char *m = getenv("BS_GPU_MATH")) {
+        if (!strcmp(m, "ieee")) cfg.math = BS_MATH_IEEE;
+        else if (!strcmp(m, "fast")) cfg.math = BS_MATH_FAST;
+        else if (!strcmp(m, "reference")) cfg.math = BS_MATH_REFERENCE;
+        else if (*m) {
+            printf("ERROR: BS_GPU_MATH must be fast, ieee or reference.\n");
+            exit(1);
+        }
+    }
     rv = bs_gpu_init_ex(&ctx, &cfg);
     const double t_init1 = now_s();
     if (rv != BS_GPU_OK) {

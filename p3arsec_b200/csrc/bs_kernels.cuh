@@ -545,6 +545,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // SHAPE 0: 16 consumer warps, 4 stages.  SHAPE 1 (fp64 only; the fp32 entry is an alias of shape 0): 24 consumer warps, 3 stages --
 // the fp64 math is issue-bound with long dependent DFMA chains, so more resident warps per scheduler hide more of its
 // fixed-latency stalls; registers are then capped at 80 per thread by the launch bounds.
+#ifndef BS_TMA_ARRIVE_ALL
+#define BS_TMA_ARRIVE_ALL 0  /* 1: every consumer thread arrives on the "empty" barrier itself (measurement / racecheck build) */
+#endif
 template <typename FP, int SHAPE> struct TmaCfg;
 template <int SHAPE> struct TmaCfg<float, SHAPE> { enum { TILE = 2048, STAGES = 4, CONSUMERS = 512 }; };  // 6 x 8 KB per stage; 192 KB per CTA, 1 CTA per SM
 template <> struct TmaCfg<double, 0> { enum { TILE = 1024, STAGES = 4, CONSUMERS = 512 }; };              // 5 x 8 KB + 4 KB per stage; 176 KB per CTA
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
     if (threadIdx.x == 0) {
         for (int st = 0; st < STAGES; st++) {
             mbar_init(&full[st], 1);                      // the producer's expect_tx arrival
-            mbar_init(&empty[st], TMA_CONSUMERS / 32);    // one arrival per consumer warp
+            mbar_init(&empty[st], BS_TMA_ARRIVE_ALL ? TMA_CONSUMERS : TMA_CONSUMERS / 32);  // one arrival per consumer warp (or thread)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -633,8 +636,16 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
                 vt[u] = reinterpret_cast<const vec *>(src + 4 * FP_TILE_BYTES)[gi];
                 vo[u] = reinterpret_cast<const ivec *>(src + 5 * FP_TILE_BYTES)[gi];
             }
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);   // stage is free again: refill overlaps our math
+            // the stage is free again (its refill overlaps our math).  One arrival per warp: the lanes' reads are ordered
+            // before lane 0's release by __syncwarp.  (compute-sanitizer racecheck does not follow that transitive
+            // ordering and reports the next round's bulk copy as a hazard against lanes 1-31; with BS_TMA_ARRIVE_ALL=1,
+            // every thread arriving for itself, it reports none -- profiles/r02_compute_sanitizer_racecheck.txt.)
+            if (BS_TMA_ARRIVE_ALL) {
+                mbar_arrive(&empty[st]);
+            } else {
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);
+            }
 #pragma unroll
             for (int u = 0; u < GPT; u++) {
                 vec p;

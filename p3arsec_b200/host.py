@@ -84,7 +84,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("BS_GPU_LIB") or LIB_PATH  # BS_GPU_LIB: an alternative build of the same ABI (measurement runs only)
     if not os.path.exists(p):
         raise ImportError("%s not found: build it with `make -C p3arsec_b200/csrc` (or __graft_entry__.build()); "
                           "p3arsec_b200 has no CPU fallback" % p)

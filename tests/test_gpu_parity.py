@@ -209,6 +209,20 @@ def test_err_chk_against_reference(name, fp_bytes, sfx):
         assert errs == 0 and gold["num_errors_line"] == "Num Errors: 0"
 
 
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_err_chk_reference_mode_gives_exactly_the_reference_verdicts(name):
+    # With BS_MATH_REFERENCE the prices ARE the reference's, so its ERR_CHK output must be reproduced with no
+    # "within rounding of the threshold" exception at all: the same offender set, the same "Num Errors" total --
+    # on edge2k too (hundreds of offenders), where the fast modes need the magnitude-scaled reading
+    inputs, d = _golden_inputs(name, 4)
+    runs = 100   # NUM_RUNS: the reference counts every offender once per run (blackscholes.c:338)
+    got, errs, bad = gpu_prices(inputs, 4, num_runs=runs, dgrefval=d["dgrefval"], err_chk=True, math=host.MATH_REFERENCE)
+    gold = json.load(open(golden_path(name, "errchk.json")))["f32"]
+    ref_bad = sorted({int(l.split()[2].rstrip(".")) for l in gold["errors_one_run"]})
+    assert bad.tolist() == ref_bad
+    assert "Num Errors: %d" % errs == gold["num_errors_line"]
+
+
 def test_err_chk_all_rows_bad_list_is_capped():
     n = 200000
     inputs = inputgen_like(n, seed=2)
@@ -542,6 +556,25 @@ def test_driver_binary_end_to_end(name, exe, sfx, fp_bytes, tmp_path):
     cnt, toks = oracle_lib.read_prices_text(out)
     assert cnt == n and all(len(t.split(".")[1]) == 18 for t in toks)
     assert_parity(np.array([float(t) for t in toks]), _golden_prices(name, sfx), fp_bytes, name)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_driver_binary_reference_math_writes_the_reference_file(name, tmp_path):
+    # BS_GPU_MATH=reference: the drop-in driver's prices file is BYTE FOR BYTE the file the reference's fp32 CPU build wrote
+    # (tests/golden/*.ref_f32.txt, produced by the compiled reference), and its ERR_CHK lines are the reference's lines
+    out = str(tmp_path / "prices.txt")
+    env = dict(os.environ, BS_GPU_MATH="reference")
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu_errchk"), "1", golden_path(name, "in.txt"), out], capture_output=True, text=True, env=env)
+    assert cp.returncode == 0, cp.stdout + cp.stderr
+    assert open(out, "rb").read() == open(golden_path(name, "ref_f32.txt"), "rb").read()
+    gold = json.load(open(golden_path(name, "errchk.json")))["f32"]
+    lines = cp.stdout.splitlines()
+    assert gold["num_errors_line"] in lines
+    mine = [l for l in lines if l.startswith("Error on ")]
+    assert sorted(set(mine)) == sorted(set(gold["errors_one_run"])) and len(mine) == 100 * len(gold["errors_one_run"])
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", golden_path(name, "in.txt"), out], capture_output=True, text=True,
+                        env=dict(os.environ, BS_GPU_MATH="bogus"))
+    assert cp.returncode == 1 and "BS_GPU_MATH" in cp.stdout
 
 
 def test_driver_binary_err_chk_and_usage(tmp_path):
