@@ -544,6 +544,17 @@ def inproc_record(n_dev, args, host, steps):
     rec["gpu_launches"] = int(launches)
     rec["what"] = "synthetic 1B-option set sharded over %d devices by ONE context, device-resident, NUM_RUNS=100" % n_dev
     rec["tail_matches_single_device"] = bool(np.array_equal(got, np.roll(single[:1000], -((nb - 1000) % 1000))))
+    # the same 1B-option set on ONE device of this box, same process, same minute: the N = 1 anchor of the strong-scaling curve
+    with host.BlackScholesGPU(nb, devices=[0], host_staging=False, with_dgrefval=False) as one_big:
+        one_big.fill_synthetic(0)
+        for _ in range(3):
+            one_big.run(NUM_RUNS)
+        ms1 = 0.0
+        for _ in range(3):
+            one_big.run(NUM_RUNS)
+            ms1 += one_big.timing()["roi_ms"]
+    rec["single_gpu_1b"] = {"value": nb * NUM_RUNS * 3 / (ms1 * 1e-3), "unit": "options/s", "ms_per_step": ms1 / 3, "steps": 3,
+                            "what": "the same 1B-option set, device-resident, on device 0 alone (this box, this process)"}
     return rec
 
 

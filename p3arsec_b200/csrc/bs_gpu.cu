@@ -207,7 +207,7 @@ template <typename FP, int SHAPE> const void *tma_kernel(int math)
     if (math == BS_MATH_IEEE) return (const void *)bsk::bs_map_tma<FP, bsk::MATH_IEEE, SHAPE>;
     return (const void *)bsk::bs_map_tma<FP, bsk::MATH_FAST, SHAPE>;
 }
-// shape of the TMA kernel: fp32 has one; fp64 has the 16-warp / 4-stage and the 24-warp / 3-stage one (tma_wide)
+// shape of the TMA kernel: fp32 has one; fp64 has three (tma_shape: 16 warps / 4 stages, 24 / 3, 16 warps x two groups / 2)
 const void *tma_kernel_ptr(const bs_gpu_ctx *c)
 {
     if (c->fp_bytes == 4) return tma_kernel<float, 0>(kernel_math(c));
@@ -1032,7 +1032,8 @@ int bs_gpu_limit_devices(int max_gpus)
     if (max_gpus < 1) return BS_GPU_ERR_INVALID;
     std::string list;
     const char *vis = getenv("CUDA_VISIBLE_DEVICES");
-    if (vis && *vis) {  // keep the first max_gpus entries of the caller's own list
+    if (vis && !*vis) return BS_GPU_OK;  // set and empty: the caller hid every device; leave it so
+    if (vis) {  // keep the first max_gpus entries of the caller's own list
         int kept = 0;
         const char *p = vis;
         while (*p && kept < max_gpus) {
@@ -1108,7 +1109,7 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     }
     // fp64 (unless the caller chose a geometry/variant explicitly): the fast-math kernel takes its inputs through the
     // bulk-copy ring (bs_map_tma: 81.0 us per 10M options = 6.42 TB/s against 85.9 us with software-pipelined LDG.128
-    // and 84.3 us for the LDG traffic probe itself, profiles/r02_tune_fp64.txt); ERR_CHK runs, which the TMA kernel
+    // and 84.3 us for the LDG traffic probe itself, profiles/r02_tune_fp64_tma.txt); ERR_CHK runs, which the TMA kernel
     // does not implement, use the software-pipelined LDG kernel.
     if (c->fp_bytes == 8 && !cfg->variant && !cfg->unroll && !cfg->threads_per_block && !cfg->blocks_per_sm && c->math == BS_MATH_FAST)
         c->variant = VARIANT_PIPE | VARIANT_TMA;

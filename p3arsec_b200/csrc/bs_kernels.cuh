@@ -546,7 +546,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // the fp64 math is issue-bound with long dependent DFMA chains, so more resident warps per scheduler hide more of its
 // fixed-latency stalls; registers are then capped at 80 per thread by the launch bounds.
 #ifndef BS_TMA_ARRIVE_ALL
-#define BS_TMA_ARRIVE_ALL 0  /* 1: every consumer thread arrives on the "empty" barrier itself (measurement / racecheck build) */
+#define BS_TMA_ARRIVE_ALL 1  /* 1 (default): every consumer thread arrives on the "empty" barrier itself; 0: one elected lane per warp */
 #endif
 template <typename FP, int SHAPE> struct TmaCfg;
 template <int SHAPE> struct TmaCfg<float, SHAPE> { enum { TILE = 2048, STAGES = 4, CONSUMERS = 512 }; };  // 6 x 8 KB per stage; 192 KB per CTA, 1 CTA per SM
@@ -636,10 +636,11 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
                 vt[u] = reinterpret_cast<const vec *>(src + 4 * FP_TILE_BYTES)[gi];
                 vo[u] = reinterpret_cast<const ivec *>(src + 5 * FP_TILE_BYTES)[gi];
             }
-            // the stage is free again (its refill overlaps our math).  One arrival per warp: the lanes' reads are ordered
-            // before lane 0's release by __syncwarp.  (compute-sanitizer racecheck does not follow that transitive
-            // ordering and reports the next round's bulk copy as a hazard against lanes 1-31; with BS_TMA_ARRIVE_ALL=1,
-            // every thread arriving for itself, it reports none -- profiles/r02_compute_sanitizer_racecheck.txt.)
+            // The stage is free again (its refill overlaps our math).  Every consumer thread releases its own reads.
+            // (One arrival per warp behind a __syncwarp is equally correct -- the lanes' reads are ordered before lane 0's
+            // release -- and equally fast, 88-90 us either way, but compute-sanitizer racecheck does not follow that
+            // transitive ordering and reports the next round's bulk copy as a hazard against lanes 1-31: 77 reports with
+            // the elected-lane form, none with this one; profiles/r02_compute_sanitizer_racecheck.txt.)
             if (BS_TMA_ARRIVE_ALL) {
                 mbar_arrive(&empty[st]);
             } else {

@@ -207,3 +207,21 @@ def test_soa_rejects_truncated_file(tmp_path):
     open(soa, "wb").write(blob[: len(blob) // 2])
     with pytest.raises(host.BsIoError):
         host.load_options(soa, 4)
+
+
+@pytest.mark.parametrize("stride", [2**64 - 4096, (2**64) // 7 + 4096, 8, 0])
+def test_soa_rejects_a_crafted_stream_stride(stride, tmp_path):
+    # a huge stream_stride must not be able to wrap the size computation of the header check (the file would
+    # then be "big enough" and the loader would copy from far outside the mapping); a stride too small for the streams
+    # is refused as well
+    import struct
+    d = host.load_options(golden_path("table1k", "in.txt"), 4)
+    soa = str(tmp_path / "t.bssoa")
+    host.write_soa(soa, d)
+    blob = bytearray(open(soa, "rb").read())
+    # SoaHeader: magic[8], u32 version, u32 fp_bytes, u64 num_options, u64 stream_stride, ...
+    assert struct.unpack_from("<Q", blob, 16)[0] == 1000
+    struct.pack_into("<Q", blob, 24, stride)
+    open(soa, "wb").write(bytes(blob))
+    with pytest.raises(host.BsIoError):
+        host.load_options(soa, 4)
