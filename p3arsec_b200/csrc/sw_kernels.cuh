@@ -394,6 +394,11 @@ SW_HOST_DEVICE constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(Fa
 #ifndef SW_TAIL_TRIP
 #define SW_TAIL_TRIP 6
 #endif
+#ifndef SW_PAIRED_RCP
+#define SW_PAIRED_RCP 0  /* 1: phase A shares one reciprocal (one MUFU seed + Newton step) per pair of central draws.  Measured
+                            neutral on B200 (12.56-12.62 against 12.62 G trials/s native: 15 MUFU.RCP64H fewer per trial, the same
+                            FP64 count, the same time -- the seeds were not what the dispatch port was waiting for), so off. */
+#endif
 #ifndef SW_PHASE_A_GROUP
 #define SW_PHASE_A_GROUP 6  /* draws evaluated side by side in phase A: 3, 6, 10, 15 or 30 */
 #endif
@@ -448,19 +453,47 @@ SW_HD void normals(const LT &tab, const double *__restrict__ tailtab, double *__
             den[i] = fma(den[i], r[i], 1.0);
             q[i] = xc[i] * num[i];
         }
+        if (SW_PAIRED_RCP && (G % 2) == 0) {
+            // one reciprocal per PAIR of draws: 1/den_a = r den_b, 1/den_b = r den_a with r = 1/(den_a den_b).  The MUFU seed
+            // is the expensive instruction here (6-8 dispatch cycles when dense, profiles/r01_dispatch_cost_microbench.txt);
+            // a pair costs the same eight FP64 instructions either way and one seed less.  den is in [0.11, 1] on the
+            // central branch (and garbage-but-finite for tail draws, whose z is overwritten below).
+            double dd[G / 2], rr[G / 2];
 #pragma unroll
-        for (int i = 0; i < G; ++i) rx[i] = bsm::seed_rcp(den[i]);       // MUFU.RCP64H
+            for (int i = 0; i < G / 2; ++i) dd[i] = den[2 * i] * den[2 * i + 1];
 #pragma unroll
-        for (int i = 0; i < G; ++i) e[i] = fma(-den[i], rx[i], 1.0);     // one cubic Newton step: x (1 + e + e^2)
+            for (int i = 0; i < G / 2; ++i) rr[i] = bsm::seed_rcp(dd[i]);    // MUFU.RCP64H
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            e[i] = fma(e[i], e[i], e[i]);
-            q[i] = q[i] * rx[i];
-        }
+            for (int i = 0; i < G / 2; ++i) e[i] = fma(-dd[i], rr[i], 1.0);  // one cubic Newton step: x (1 + e + e^2)
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            z[(k0 + i) * THREADS + tid] = fma(q[i], e[i], q[i]);  // garbage for tail draws: overwritten below
-            if ((sg[i] - S_LO) > (S_HI - S_LO)) tail |= 1u << (k0 + i);
+            for (int i = 0; i < G / 2; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) rr[i] = fma(rr[i], e[i], rr[i]);
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+                rx[2 * i] = rr[i] * den[2 * i + 1];
+                rx[2 * i + 1] = rr[i] * den[2 * i];
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                z[(k0 + i) * THREADS + tid] = q[i] * rx[i];  // garbage for tail draws: overwritten below
+                if ((sg[i] - S_LO) > (S_HI - S_LO)) tail |= 1u << (k0 + i);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i) rx[i] = bsm::seed_rcp(den[i]);       // MUFU.RCP64H
+#pragma unroll
+            for (int i = 0; i < G; ++i) e[i] = fma(-den[i], rx[i], 1.0);     // one cubic Newton step: x (1 + e + e^2)
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                e[i] = fma(e[i], e[i], e[i]);
+                q[i] = q[i] * rx[i];
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                z[(k0 + i) * THREADS + tid] = fma(q[i], e[i], q[i]);  // garbage for tail draws: overwritten below
+                if ((sg[i] - S_LO) > (S_HI - S_LO)) tail |= 1u << (k0 + i);
+            }
         }
     }
     while (tail) {

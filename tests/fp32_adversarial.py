@@ -14,7 +14,10 @@ GPU through the C ABI and with the oracle (bit-identical to the compiled referen
 for BS_MATH_FAST, BS_MATH_IEEE and BS_MATH_REFERENCE, and records the worst |delta| per mode and domain together with
 the option that produced it.  Prints one JSON object (and writes it to --out).
 
-    python tools/fp32_adversarial.py [--random-millions 200] [--out gpurun_out/r02_fp32_adversarial.json]
+    python tests/fp32_adversarial.py [--random-millions 200] [--out gpurun_out/r02_fp32_adversarial.json]
+
+It lives under tests/ because it is a checker: it calls the oracle (tests/oracle_lib.py), which only tests may do.
+tests/test_gpu_parity.py::test_fp32_adversarial_sweep_reduced runs one slice of domain A on every GPU test run.
 """
 import argparse
 import json
@@ -26,7 +29,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracle_lib: this tool is a checker, not product code
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 RATES = np.array([0.0250, 0.0275, 0.0500, 0.0750, 0.1000])
 SPOTS = np.array([20.00, 20.01, 33.33, 50.00, 64.00, 99.99, 100.00, 120.00])
@@ -71,7 +74,7 @@ def main():
     from p3arsec_b200 import host
 
     modes = (("fast", host.MATH_FAST), ("ieee", host.MATH_IEEE), ("reference", host.MATH_REFERENCE))
-    report = {"tool": "tools/fp32_adversarial.py", "bound": 1e-4, "domains": {}}
+    report = {"tool": "tests/fp32_adversarial.py", "bound": 1e-4, "domains": {}}
     t0 = time.time()
     for dom, gen, desc in (
             ("A_inputgen_structured", lambda: sweep(True), "v,t on the 2-decimal grid x 5 rates x 8 spots x d1 in [-6,6] (49 strikes), strike/spot clipped to 0.7..1.3, calls+puts"),

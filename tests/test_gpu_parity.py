@@ -371,6 +371,20 @@ def test_fp32_reference_mode_native_10m():
     assert worst == 0.0 and exact == 1.0
 
 
+def test_fp32_adversarial_sweep_reduced():
+    # one slice (one rate, calls and puts: 4.6M options) of the structured sweep of tests/fp32_adversarial.py -- every (v, t) of
+    # the inputgen grid x 8 spots x d1 in [-6, 6] -- in all three modes; the full 246M-option sweep is profiles/r02_fp32_adversarial.json
+    import fp32_adversarial as adv
+    gen = adv.sweep(True)
+    for _ in range(2):
+        inputs = next(gen)
+        ref = oracle_prices(inputs, 4).astype(np.float64)
+        for math, bound in ((host.MATH_FAST, 9e-5), (host.MATH_IEEE, 9e-5), (host.MATH_REFERENCE, 0.0)):
+            got, _, _ = gpu_prices(inputs, 4, math=math, with_dgrefval=False)
+            worst = float(np.abs(got.astype(np.float64) - ref).max())
+            assert worst <= bound, (math, worst)
+
+
 def test_fp32_reference_mode_err_chk_and_sizes():
     for n in (1, 3, 5, 257, 65537):
         inputs = inputgen_like(n, seed=n + 100)
