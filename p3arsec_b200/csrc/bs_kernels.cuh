@@ -394,9 +394,9 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
 
     // the fp64 fast math reads two 64-entry tables (bs_math_f64.h) from shared memory; other variants carry 8 bytes
     enum { USE_TAB = (sizeof(FP) == 8 && MATH == MATH_FAST) ? 1 : 0 };
-    __shared__ double s_tab[USE_TAB ? bsm::TAB_DOUBLES : 1];
+    __shared__ double s_tab[USE_TAB ? bsm::TAB256_DOUBLES : 1];
     if (USE_TAB) {
-        bsm::fill_tables(s_tab, (int)threadIdx.x, (int)blockDim.x);
+        bsm::fill_tables256(s_tab, (int)threadIdx.x, (int)blockDim.x);
         __syncthreads();
     }
     const double *tab = s_tab;
@@ -561,7 +561,7 @@ template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_stage
 template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_smem_bytes()
 {
     return tma_stage_bytes<FP, SHAPE>() * TmaCfg<FP, SHAPE>::STAGES + 2 * TmaCfg<FP, SHAPE>::STAGES * sizeof(uint64_t) + 128 +
-           ((sizeof(FP) == 8) ? bsm::TAB_DOUBLES * sizeof(double) : 0);
+           ((sizeof(FP) == 8) ? bsm::TAB256_DOUBLES * sizeof(double) : 0);
 }
 template <typename FP, int SHAPE> __host__ __device__ constexpr int tma_threads() { return TmaCfg<FP, SHAPE>::CONSUMERS + 32; }
 
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (USE_TAB) bsm::fill_tables(s_tab, (int)threadIdx.x, (int)blockDim.x);
+    if (USE_TAB) bsm::fill_tables256(s_tab, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
 
     if (warp == TMA_CONSUMERS / 32) {

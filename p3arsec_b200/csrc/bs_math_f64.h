@@ -119,6 +119,18 @@ BS_HD void fill_tables(double *tab, int first, int step)
         tab[i] = from_bits(i < TAB_LOG ? EXP2_64_BITS[i] : LOG_RC_LC_BITS[(i - TAB_LOG) >> 1][(i - TAB_LOG) & 1]);
 }
 
+// The blackscholes fp64 kernel's own, four times finer tables (6 KB): [0,256) = 2^(j/256); then 256 pairs {1/c_i, log c_i
+// (- ln2 for i >= LOG256_SPLIT)}.  Finer intervals buy shorter polynomials -- degree 4 instead of 5 for exp (|r| <= ln2/512:
+// r^5/120 < 4e-17), degree 5 instead of 7 for log (|r| < 2^-9: r^6/6 < 1e-17) -- i.e. four FP64 instructions less per option
+// at the same accuracy; the kernel is FP64-issue- and, sustained, power-bound.
+enum { TAB256_EXP = 0, TAB256_LOG = 256, TAB256_DOUBLES = 256 + 512 };
+
+BS_HD void fill_tables256(double *tab, int first, int step)
+{
+    for (int i = first; i < TAB256_DOUBLES; i += step)
+        tab[i] = from_bits(i < TAB256_LOG ? EXP2_256_BITS[i] : LOG256_RC_LC_BITS[(i - TAB256_LOG) >> 1][(i - TAB256_LOG) & 1]);
+}
+
 // exp(x) for x <= ~700 (the Map only needs x <= 0): exact zero below -708 (no subnormal results).
 BS_HD double exp_f64(double x, const double *tab)
 {
@@ -196,6 +208,39 @@ BS_HD double exp_core_f64(double x, const double *tab)
     return scale_by_pow2(fma(T, em1, T), n >> 6);  // the mantissa product is in [0.99, 2.0)
 }
 
+// exp(x), |x| < 700, from the 256-entry table: 9 FP64 instructions.  `tab` is the block filled by fill_tables256.
+BS_HD double exp256_core_f64(double x, const double *tab)
+{
+    const double MAGIC = 6755399441055744.0;  // 2^52 + 2^51
+    double nd = fma(x, kd(K_EXP256_INV), MAGIC);
+    const int n = (int)(uint32_t)to_bits(nd);  // round(x * 256/ln2) = 256 k + j
+    nd -= MAGIC;
+    double r = fma(nd, -kd(K_EXP256_HI), x);
+    r = fma(nd, -kd(K_EXP256_LO), r);            // |r| <= ln2/512
+    double q = fma(kd(K_EXP_C4), r, kd(K_EXP_C3));
+    q = fma(q, r, 0.5);
+    const double em1 = fma(q, r * r, r);         // r + r^2/2 + r^3/6 + r^4/24
+    const double T = tab[TAB256_EXP + (n & 255)];
+    return scale_by_pow2(fma(T, em1, T), n >> 8);
+}
+
+// log(x) for normal x > 0 from the 256-entry table: 9 FP64 instructions.
+BS_HD double log256_f64(double x, const double *tab)
+{
+    const uint64_t b = to_bits(x);
+    const int i = (int)(b >> 44) & 255;          // top 8 mantissa bits: m in [1 + i/256, 1 + (i+1)/256)
+    const int e = (int)(b >> 52) - 1023 + (i >= LOG256_SPLIT ? 1 : 0);
+    const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+    const double rc = tab[TAB256_LOG + 2 * i], lc = tab[TAB256_LOG + 2 * i + 1];
+    const double r = fma(m, rc, -1.0);           // |r| < 2^-9
+    double q = fma(kd(K_LOG_C5), r, -0.25);      // r - r^2/2 + r^3/3 - r^4/4 + r^5/5
+    q = fma(q, r, kd(K_LOG_C3));
+    q = fma(q, r, -0.5);
+    const double lp = fma(r * r, q, r);          // log1p(r)
+    const double ed = (double)e;
+    return fma(ed, kd(K_LN2_HI), lc + fma(ed, kd(K_LN2_LO), lp));
+}
+
 // poly(k) with k = 1/(1 + 0.2316419|d|): the CNDF tail 1 - N(|d|) is exp(-d^2/2) k poly(k) / sqrt(2 pi); the constants
 // of CNDF (blackscholes.c:126,:156,:164-170) are pre-multiplied by 1/sqrt(2 pi).
 BS_HD double cndf_poly_f64(double k)
@@ -224,7 +269,7 @@ BS_HD double cndf_tail_f64(double d, double k, const double *tab)
 //         s N1 - fv N2 = g (+-P1 -+ P2) + ([N1 = 1 - w1] s - [N2 = 1 - w2] fv):
 //     one exponential, signs and the two optional terms selected by integer masks on the sign bits of d1, d2;
 //   * one shared reciprocal for the two CNDF arguments (as before).
-// 76 fp64 operations per option (94 before).  Rounding errors of d1 enter the price only multiplied by den (the
+// With the 256-entry tables (exp256_core_f64, log256_f64): 72 fp64 operations per option (94 in round 1).  Rounding errors of d1 enter the price only multiplied by den (the
 // common shift of d1 and d2 cancels in the identity), i.e. at the 1e-15 level: measured 8e-14 worst absolute
 // distance to the fp64 CPU build on the inputgen table (tests/test_math_f64.py, tests/test_gpu_parity.py).
 BS_HD double price_f64_fast(double s, double k, double r, double v, double t, int otype, bool *ok, const double *tab)
@@ -236,16 +281,16 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double sq = t * y;                     // sqrt t                        :224
     const double den = v * sq;                   // xDen                          :238
     const double sk = s * (R * den);             // s/k
-    const double lg = log_f64(sk, tab);          // log(s/k)                      :226
+    const double lg = log256_f64(sk, tab);       // log(s/k)                      :226   (tab: fill_tables256)
     const double drift = fma(0.5 * v, v, r);     // r + v^2/2                     :231-234
     const double d1 = fma(drift, t, lg) * rden;  //                               :235-239
     const double d2 = d1 - den;                  //                               :240
     const double rt = r * t;
-    const double fv = k * exp_core_f64(-rt, tab);  // strike exp(-r t)            :248
+    const double fv = k * exp256_core_f64(-rt, tab);  // strike exp(-r t)         :248
     const double a1 = fma(fabs(d1), kd(K_CNDF_C), 1.0), a2 = fma(fabs(d2), kd(K_CNDF_C), 1.0);
     const double a12 = a1 * a2;
     const double rab = rcp_f64(a12);             // one reciprocal serves both CNDF arguments   :156-158
-    const double g = s * exp_core_f64((-0.5 * d1) * d1, tab);  // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
+    const double g = s * exp256_core_f64((-0.5 * d1) * d1, tab);  // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
     const double P1 = cndf_poly_f64(rab * a2), P2 = cndf_poly_f64(rab * a1);
     // N(x) = tail w for x < 0 and 1 - w otherwise; a put needs N(-x): the tail itself is wanted when sign(d) != put.   :249-255
     const uint64_t SIGN = 0x8000000000000000ull;

@@ -26,6 +26,9 @@ def test_building_blocks_within_a_few_ulp(checker):
     assert float(out["rcp"]) <= 1.0 and float(out["rsqrt"]) <= 1.5
     assert float(out["exp"]) <= 1.5 and float(out["exp_small"]) <= 1.0
     assert float(out["exp_pair_pos"]) <= 1.5 and float(out["exp_pair_neg"]) <= 1.5
+    # the 256-entry blocks the blackscholes fp64 kernel uses (one / two polynomial degrees less)
+    assert float(out["exp256"]) <= 1.5 and float(out["log256"]) <= 1.5 and float(out["log256_near_1_abs"]) <= 0.1
+    assert float(out["exp256_0"]) == 1.0 and abs(float(out["log256_1"])) < 1e-17
     # log feeds d1 = (drift*t + log(s/k)) / den: its ABSOLUTE error matters, measured in ulps of max(1, |log x|)
     assert float(out["log"]) <= 1.5 and float(out["log_near_1_abs"]) <= 0.1
     assert float(out["exp_below_-708"]) == 0.0 and float(out["exp_0"]) == 1.0 and abs(float(out["log_1"])) < 1e-17

@@ -21,6 +21,7 @@ static double ulps(double got, long double ref)
 }
 
 static double TAB[bsm::TAB_DOUBLES];
+static double TAB256[bsm::TAB256_DOUBLES];
 
 // absolute error in units of ulp(max(1, |ref|)): what matters for log feeding d1
 static double abs_units(double got, long double ref)
@@ -34,12 +35,13 @@ static double abs_units(double got, long double ref)
 int main(int argc, char **argv)
 {
     bsm::fill_tables(TAB, 0, 1);
+    bsm::fill_tables256(TAB256, 0, 1);
     if (argc > 1 && !strcmp(argv[1], "price")) {
         double s, k, r, v, t;
         int o;
         while (scanf("%lf %lf %lf %lf %lf %d", &s, &k, &r, &v, &t, &o) == 6) {
             bool ok;
-            double p = bsm::price_f64_fast(s, k, r, v, t, o, &ok, TAB);
+            double p = bsm::price_f64_fast(s, k, r, v, t, o, &ok, TAB256);
             printf("%.17g %d\n", p, ok ? 1 : 0);
         }
         return 0;
@@ -68,6 +70,18 @@ int main(int argc, char **argv)
         w_pn = fmax(w_pn, ulps(en, expl(-(long double)x)));
     }
     printf("exp_pair_pos %.3f\nexp_pair_neg %.3f\n", w_pp, w_pn);
+    // the 256-entry blocks of the blackscholes fp64 kernel
+    double w_e256 = 0, w_l256 = 0, w_l256_near1 = 0;
+    for (int i = 0; i < N; i++) {
+        double x = (u01(rng) - 0.5) * (i % 4 == 0 ? 1000.0 : 80.0);
+        w_e256 = fmax(w_e256, ulps(bsm::exp256_core_f64(x, TAB256), expl((long double)x)));
+        double b = exp((u01(rng) - 0.5) * 60.0);
+        w_l256 = fmax(w_l256, abs_units(bsm::log256_f64(b, TAB256), logl((long double)b)));
+        double c1 = 1.0 + (u01(rng) - 0.5) * 2e-3;
+        if (c1 != 1.0) w_l256_near1 = fmax(w_l256_near1, abs_units(bsm::log256_f64(c1, TAB256), logl((long double)c1)));
+    }
+    printf("exp256 %.3f\nlog256 %.3f\nlog256_near_1_abs %.3f\nexp256_0 %.17g\nlog256_1 %.17g\n", w_e256, w_l256, w_l256_near1,
+           bsm::exp256_core_f64(0.0, TAB256), bsm::log256_f64(1.0, TAB256));
     printf("exp_below_-708 %g\nexp_0 %.17g\nlog_1 %.17g\n", bsm::exp_f64(-709.5, TAB), bsm::exp_f64(0.0, TAB), bsm::log_f64(1.0, TAB));
     // log(x) for x within 1e-3 of 1, error relative to the result
     double w_log1 = 0;
