@@ -385,6 +385,42 @@ struct Group {
 template <int MATH> __device__ __forceinline__ float price_any(float s, float k, float r, float v, float t, int o, const double *) { return price_f32<MATH>(s, k, r, v, t, o); }
 template <int MATH> __device__ __forceinline__ double price_any(double s, double k, double r, double v, double t, int o, const double *tab) { return price_f64_any<MATH>(s, k, r, v, t, o, tab); }
 
+// One group (4 fp32 / 2 fp64 options) priced lane by lane.  The fp64 fast path defers its degenerate-input test until every
+// lane has been evaluated (BS_F64_GROUP_ILP, default on): one branch per group instead of one per option, so the lanes' long
+// dependent FP64 chains share a basic block and the compiler interleaves them (the fp64 kernel's top stall is `wait`, the
+// fixed-latency dependency stall, at four warps per scheduler; profiles/r02_ncu_f64_fast_tma_tab256.txt).
+#ifndef BS_F64_GROUP_ILP
+#define BS_F64_GROUP_ILP 1
+#endif
+template <int MATH, typename FP>
+__device__ __forceinline__ typename VT<FP>::vec price_group(const typename VT<FP>::vec &s, const typename VT<FP>::vec &k, const typename VT<FP>::vec &r,
+                                                            const typename VT<FP>::vec &v, const typename VT<FP>::vec &t,
+                                                            const typename VT<FP>::ivec &o, const double *tab)
+{
+    typename VT<FP>::vec p;
+    if constexpr (sizeof(FP) == 8 && MATH == MATH_FAST && BS_F64_GROUP_ILP) {
+        bool ok[VT<FP>::LANES];
+        bool all = true;
+#pragma unroll
+        for (int l = 0; l < VT<FP>::LANES; l++) {
+            set_lane(p, l, (FP)bsm::price_f64_fast((double)lane(s, l), (double)lane(k, l), (double)lane(r, l), (double)lane(v, l), (double)lane(t, l),
+                                                   lane(o, l), &ok[l], tab));
+            all = all && ok[l];
+        }
+        if (__builtin_expect(!all, 0)) {
+#pragma unroll
+            for (int l = 0; l < VT<FP>::LANES; l++)
+                if (!ok[l])
+                    set_lane(p, l, (FP)price_f64_cold((double)lane(s, l), (double)lane(k, l), (double)lane(r, l), (double)lane(v, l), (double)lane(t, l), lane(o, l)));
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < VT<FP>::LANES; l++) set_lane(p, l, price_any<MATH>(lane(s, l), lane(k, l), lane(r, l), lane(v, l), lane(t, l), lane(o, l), tab));
+    }
+    return p;
+}
+
+
 template <typename FP, int MATH, int UNROLL, bool CHK, bool PIPE>
 __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec)
 {
@@ -394,9 +430,9 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
 
     // the fp64 fast math reads two 64-entry tables (bs_math_f64.h) from shared memory; other variants carry 8 bytes
     enum { USE_TAB = (sizeof(FP) == 8 && MATH == MATH_FAST) ? 1 : 0 };
-    __shared__ double s_tab[USE_TAB ? bsm::TAB256_DOUBLES : 1];
+    __shared__ double s_tab[USE_TAB ? bsm::BS_F64_TAB_DOUBLES : 1];
     if (USE_TAB) {
-        bsm::fill_tables256(s_tab, (int)threadIdx.x, (int)blockDim.x);
+        bsm::BS_F64_FILL_TABLES(s_tab, (int)threadIdx.x, (int)blockDim.x);
         __syncthreads();
     }
     const double *tab = s_tab;
@@ -436,11 +472,7 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
         for (int u = 0; u < UNROLL; u++) {
             const size_t gi = g0 + u * stride;
             if (u == 0 || gi < groups) {
-                vec p;
-#pragma unroll
-                for (int l = 0; l < LANES; l++)
-                    set_lane(p, l, price_any<MATH>(lane(src[u].s, l), lane(src[u].k, l), lane(src[u].r, l), lane(src[u].v, l),
-                                                   lane(src[u].t, l), lane(src[u].o, l), tab));
+                const vec p = price_group<MATH, FP>(src[u].s, src[u].k, src[u].r, src[u].v, src[u].t, src[u].o, tab);
                 st_stream(p_out + gi, p);
                 if (CHK) {
 #pragma unroll
@@ -561,7 +593,7 @@ template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_stage
 template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_smem_bytes()
 {
     return tma_stage_bytes<FP, SHAPE>() * TmaCfg<FP, SHAPE>::STAGES + 2 * TmaCfg<FP, SHAPE>::STAGES * sizeof(uint64_t) + 128 +
-           ((sizeof(FP) == 8) ? bsm::TAB256_DOUBLES * sizeof(double) : 0);
+           ((sizeof(FP) == 8) ? bsm::BS_F64_TAB_DOUBLES * sizeof(double) : 0);
 }
 template <typename FP, int SHAPE> __host__ __device__ constexpr int tma_threads() { return TmaCfg<FP, SHAPE>::CONSUMERS + 32; }
 
@@ -591,7 +623,7 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (USE_TAB) bsm::fill_tables256(s_tab, (int)threadIdx.x, (int)blockDim.x);
+    if (USE_TAB) bsm::BS_F64_FILL_TABLES(s_tab, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
 
     if (warp == TMA_CONSUMERS / 32) {
@@ -649,10 +681,7 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
             }
 #pragma unroll
             for (int u = 0; u < GPT; u++) {
-                vec p;
-#pragma unroll
-                for (int l = 0; l < LANES; l++)
-                    set_lane(p, l, price_any<MATH>(lane(vs[u], l), lane(vk[u], l), lane(vr[u], l), lane(vv[u], l), lane(vt[u], l), lane(vo[u], l), s_tab));
+                const vec p = price_group<MATH, FP>(vs[u], vk[u], vr[u], vv[u], vt[u], vo[u], s_tab);
                 st_stream(p_out + t * GROUPS + threadIdx.x + u * TMA_CONSUMERS, p);
             }
         }

@@ -241,6 +241,23 @@ BS_HD double log256_f64(double x, const double *tab)
     return fma(ed, kd(K_LN2_HI), lc + fma(ed, kd(K_LN2_LO), lp));
 }
 
+// Which tables the blackscholes fp64 kernel uses: the 256-entry ones (default) or, for A/B measurements on one board
+// (-DBS_F64_TAB64=1, lib/libbs_gpu_tab64.so), the 64-entry ones it shares with the swaptions kernels.
+#ifndef BS_F64_TAB64
+#define BS_F64_TAB64 0
+#endif
+#if BS_F64_TAB64
+#define BS_F64_LOG log_f64
+#define BS_F64_EXP exp_core_f64
+#define BS_F64_FILL_TABLES fill_tables
+enum { BS_F64_TAB_DOUBLES = TAB_DOUBLES };
+#else
+#define BS_F64_LOG log256_f64
+#define BS_F64_EXP exp256_core_f64
+#define BS_F64_FILL_TABLES fill_tables256
+enum { BS_F64_TAB_DOUBLES = TAB256_DOUBLES };
+#endif
+
 // poly(k) with k = 1/(1 + 0.2316419|d|): the CNDF tail 1 - N(|d|) is exp(-d^2/2) k poly(k) / sqrt(2 pi); the constants
 // of CNDF (blackscholes.c:126,:156,:164-170) are pre-multiplied by 1/sqrt(2 pi).
 BS_HD double cndf_poly_f64(double k)
@@ -262,35 +279,33 @@ BS_HD double cndf_tail_f64(double d, double k, const double *tab)
 // inputs outside the domain of the blocks below: the caller then uses the IEEE-order path.
 //
 // Restructured for the fp64 pipe -- the kernel is bound by FP64 issue, not by HBM (profiles/r02_ncu_f64_*.txt):
-//   * ONE rsqrt, of (k v)^2 t, yields 1/(v sqrt t), 1/sqrt t, sqrt t and 1/k by multiplications;
+//   * xDen and 1/xDen from ONE rsqrt of xDen^2 = v^2 t (sqrt t itself is never needed), and the numerator of d1 as
+//     r t + xDen^2 / 2 + log(s/k) with the r t that exp(-r t) needs anyway; s/k through a 3-instruction reciprocal;
 //   * the second CNDF exponential is never evaluated.  With P_j = k_j poly(k_j) the two tails are
 //     w1 = e1 P1 and w2 = e2 P2, e_j = exp(-d_j^2/2), and the Black-Scholes identity  s n(d1) = fv n(d2)
 //     (d1 den - den^2/2 = log(s/k) + r t exactly) gives  fv w2 = s e1 P2.  Hence, with g = s e1,
 //         s N1 - fv N2 = g (+-P1 -+ P2) + ([N1 = 1 - w1] s - [N2 = 1 - w2] fv):
 //     one exponential, signs and the two optional terms selected by integer masks on the sign bits of d1, d2;
 //   * one shared reciprocal for the two CNDF arguments (as before).
-// With the 256-entry tables (exp256_core_f64, log256_f64): 72 fp64 operations per option (94 in round 1).  Rounding errors of d1 enter the price only multiplied by den (the
+// With the 256-entry tables (exp256_core_f64, log256_f64): 69 fp64 operations per option (94 in round 1).  Rounding errors of d1 enter the price only multiplied by den (the
 // common shift of d1 and d2 cancels in the identity), i.e. at the 1e-15 level: measured 8e-14 worst absolute
 // distance to the fp64 CPU build on the inputgen table (tests/test_math_f64.py, tests/test_gpu_parity.py).
 BS_HD double price_f64_fast(double s, double k, double r, double v, double t, int otype, bool *ok, const double *tab)
 {
-    const double kv = k * v;
-    const double R = rsqrt_f64((kv * kv) * t);   // 1/(k v sqrt t)
-    const double rden = R * k;                   // 1/(v sqrt t)
-    const double y = rden * v;                   // 1/sqrt t
-    const double sq = t * y;                     // sqrt t                        :224
-    const double den = v * sq;                   // xDen                          :238
-    const double sk = s * (R * den);             // s/k
-    const double lg = log256_f64(sk, tab);       // log(s/k)                      :226   (tab: fill_tables256)
-    const double drift = fma(0.5 * v, v, r);     // r + v^2/2                     :231-234
-    const double d1 = fma(drift, t, lg) * rden;  //                               :235-239
-    const double d2 = d1 - den;                  //                               :240
+    const double vv = v * v;
+    const double z = vv * t;                     // xDen^2 = v^2 t
+    const double rden = rsqrt_f64(z);            // 1/(v sqrt t)   (v > 0: checked below)
+    const double den = z * rden;                 // xDen = v sqrt t               :224,:238
+    const double sk = s * rcp_f64(k);            // s/k
+    const double lg = BS_F64_LOG(sk, tab);       // log(s/k)                      :226   (tab: BS_F64_FILL_TABLES)
     const double rt = r * t;
-    const double fv = k * exp256_core_f64(-rt, tab);  // strike exp(-r t)         :248
+    const double d1 = (fma(0.5, z, rt) + lg) * rden;  // ((r + v^2/2) t + log(s/k)) / xDen   :231-239
+    const double d2 = d1 - den;                  //                               :240
+    const double fv = k * BS_F64_EXP(-rt, tab);  // strike exp(-r t)              :248
     const double a1 = fma(fabs(d1), kd(K_CNDF_C), 1.0), a2 = fma(fabs(d2), kd(K_CNDF_C), 1.0);
     const double a12 = a1 * a2;
     const double rab = rcp_f64(a12);             // one reciprocal serves both CNDF arguments   :156-158
-    const double g = s * exp256_core_f64((-0.5 * d1) * d1, tab);  // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
+    const double g = s * BS_F64_EXP((-0.5 * d1) * d1, tab);  // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
     const double P1 = cndf_poly_f64(rab * a2), P2 = cndf_poly_f64(rab * a1);
     // N(x) = tail w for x < 0 and 1 - w otherwise; a put needs N(-x): the tail itself is wanted when sign(d) != put.   :249-255
     const uint64_t SIGN = 0x8000000000000000ull;
@@ -304,14 +319,15 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double c = fma(g, t1 - t2, bs - bf);
     // Domain of the blocks above (integer range checks on the high words; everything else -- t = 0, v = 0, s <= 0,
     // NaN, inf, denormals, overflow -- is left to the IEEE-order path, which reproduces the reference's inf/NaN results):
-    //   t, k v and s/k positive normal numbers in [2^-255, 2^256): (k v)^2 t stays normal;
+    //   v, v^2 t and s/k positive normal numbers in [2^-255, 2^256) (v^2 stays normal; t > 0 follows; a k the reciprocal
+    //              block cannot invert -- zero, denormal, >= 2^1022, inf, NaN -- yields s/k = 0, inf or NaN);
     //   |d1| < 37: exp(-d1^2/2) has not underflowed, so expressing the second tail through it loses nothing
     //              (inside the inputgen range |d1| <= 32);
     //   a1 a2 = (1 + c|d1|)(1 + c|d2|) finite: the shared reciprocal is not 0 * inf (v below ~1e-154);
     //   |r t| < 512: the exponent arithmetic of exp_core_f64 cannot wrap (the reference returns inf / NaN there).
     const uint32_t LO = 0x30000000u, SPAN = 0x20000000u;
     const uint32_t hi_d1 = (uint32_t)(to_bits(d1) >> 32) & 0x7fffffffu, hi_rt = (uint32_t)(to_bits(rt) >> 32) & 0x7fffffffu;
-    *ok = ((uint32_t)(to_bits(t) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(kv) >> 32) - LO < SPAN) &&
+    *ok = ((uint32_t)(to_bits(v) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(z) >> 32) - LO < SPAN) &&
           ((uint32_t)(to_bits(sk) >> 32) - LO < SPAN) && (hi_d1 < 0x40428000u) && ((uint32_t)(to_bits(a12) >> 32) < 0x6ff00000u) &&
           (hi_rt < 0x40800000u);
     return from_bits(to_bits(c) ^ putm);   // put: fv N(-d2) - s N(-d1) = -(s N(-d1) - fv N(-d2))
