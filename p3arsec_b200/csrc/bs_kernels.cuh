@@ -385,12 +385,13 @@ struct Group {
 template <int MATH> __device__ __forceinline__ float price_any(float s, float k, float r, float v, float t, int o, const double *) { return price_f32<MATH>(s, k, r, v, t, o); }
 template <int MATH> __device__ __forceinline__ double price_any(double s, double k, double r, double v, double t, int o, const double *tab) { return price_f64_any<MATH>(s, k, r, v, t, o, tab); }
 
-// One group (4 fp32 / 2 fp64 options) priced lane by lane.  The fp64 fast path defers its degenerate-input test until every
-// lane has been evaluated (BS_F64_GROUP_ILP, default on): one branch per group instead of one per option, so the lanes' long
-// dependent FP64 chains share a basic block and the compiler interleaves them (the fp64 kernel's top stall is `wait`, the
-// fixed-latency dependency stall, at four warps per scheduler; profiles/r02_ncu_f64_fast_tma_tab256.txt).
+// One group (4 fp32 / 2 fp64 options) priced lane by lane.  BS_F64_GROUP_ILP = 1 makes the fp64 fast path defer its
+// degenerate-input test until every lane has been evaluated: one branch per group instead of one per option, so that the
+// lanes' dependent FP64 chains share a basic block and the compiler interleaves them.  Measured on B200 (profiles/
+// r02_tune_fp64_ilp.txt): 110.9-111.1 G options/s sustained against 112.7-113.0 with one branch per option (six more
+// registers and a longer loop; the warps of the other schedulers already fill the `wait` slots), so it is off.
 #ifndef BS_F64_GROUP_ILP
-#define BS_F64_GROUP_ILP 1
+#define BS_F64_GROUP_ILP 0
 #endif
 template <int MATH, typename FP>
 __device__ __forceinline__ typename VT<FP>::vec price_group(const typename VT<FP>::vec &s, const typename VT<FP>::vec &k, const typename VT<FP>::vec &r,
