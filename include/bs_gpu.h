@@ -78,7 +78,7 @@ typedef enum bs_gpu_buffer {
  *         number of ulps, i.e. the bound scales as 1e-4 * max(1, max(spot, strike) / 128): a price near 1000 is
  *         itself quantised to 6e-5 in fp32 and the reference's own fp32 build is 1.7e-4 from its fp64 build there.
  *   fp64: |delta| <= 1e-9 * |reference| + 1e-12 in every mode (FAST: ~2 ulp building blocks; IEEE: only the last
- *         ulp of exp()/log() can differ from the fp64 CPU build). */
+ *         ulp of exp()/log() can differ from the fp64 CPU build; REFERENCE: bit-identical to it). */
 typedef enum bs_gpu_math {
     BS_MATH_DEFAULT = 0,  /* the library's default: BS_MATH_FAST (fp32 and fp64)                                  */
     BS_MATH_IEEE = 1,     /* libdevice exp/log/sqrt and IEEE-rounded divides, reference operation order; fp32 is
@@ -90,7 +90,9 @@ typedef enum bs_gpu_math {
                              promotions (blackscholes.c:154-158,164-175,232,252-253), every operation individually
                              rounded, expf/logf = glibc 2.39's algorithms (csrc/bs_libm_f32.h, pinned against the
                              host libm over all 2^32 floats): the reference CPU prices, bit for bit.  The validation
-                             mode: several times slower than FAST.  fp64: identical to BS_MATH_IEEE               */
+                             mode: several times slower than FAST.  fp64: the operation order of BS_MATH_IEEE
+                             with exp/log = glibc 2.39's double algorithms (csrc/bs_libm_f64.h, pinned against the
+                             host libm on 2 x 10^9 arguments per function): the fp64 CPU prices, bit for bit      */
 } bs_gpu_math;
 
 /* bs_gpu_config.flags */

@@ -151,7 +151,8 @@ int main(int argc, char **argv)
     cfg.num_gpus = wantGpus;
     cfg.flags = BS_GPU_FLAG_WITH_DGREFVAL;
     // BS_GPU_MATH=fast|ieee|reference selects the math mode (include/bs_gpu.h); with "reference" the prices file is byte for
-    // byte the one the reference's fp32 CPU build writes (its double-literal promotions and glibc's expf/logf reproduced)
+    // byte the one the reference's CPU build of the same fptype writes (fp32: its double-literal promotions and glibc's
+    // expf/logf reproduced; fp64: glibc's exp/log)
     if (const char *m = getenv("BS_GPU_MATH")) {
         if (!strcmp(m, "ieee")) cfg.math = BS_MATH_IEEE;
         else if (!strcmp(m, "fast")) cfg.math = BS_MATH_FAST;

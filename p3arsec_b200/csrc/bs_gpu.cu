@@ -197,7 +197,6 @@ void (*pick_kernel(int math, int unroll, bool chk, bool pipe))(bsk::Streams<FP>,
 int kernel_math(const bs_gpu_ctx *c)
 {
     if (c->variant & VARIANT_PROBE) return (int)bsk::MATH_PROBE;
-    if (c->math == BS_MATH_REFERENCE && c->fp_bytes == 8) return BS_MATH_IEEE;  // fptype=double: nothing is promoted
     return c->math;
 }
 bool use_tma(const bs_gpu_ctx *c, bool chk) { return (c->variant & VARIANT_TMA) && !chk && c->math != BS_MATH_REFERENCE; }

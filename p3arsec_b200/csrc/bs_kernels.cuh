@@ -32,6 +32,7 @@
 #include <stdint.h>
 
 #include "bs_libm_f32.h"
+#include "bs_libm_f64.h"
 #include "bs_math_f64.h"
 
 namespace bsk {
@@ -255,13 +256,20 @@ __device__ __forceinline__ float price_f32(float s, float k, float r, float v, f
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp64: reference operation order, every operation individually rounded (no FMA contraction)
+// fp64: reference operation order, every operation individually rounded (no FMA contraction).
+// GLIBC = false (BS_MATH_IEEE): libdevice exp/log -- the last ulp of those two can differ from the CPU build's libm.
+// GLIBC = true (BS_MATH_REFERENCE): glibc 2.39's own exp/log restated bit-exactly (bs_libm_f64.h) -- the prices are the
+// reference CPU prices bit for bit (sqrt and the divisions are correctly rounded on both sides).
 // ---------------------------------------------------------------------------------------------
+template <bool GLIBC> __device__ __forceinline__ double exp_ref64(double x) { return GLIBC ? bsl64::exp_glibc(x) : exp(x); }
+template <bool GLIBC> __device__ __forceinline__ double log_ref64(double x) { return GLIBC ? bsl64::log_glibc(x) : log(x); }
+
+template <bool GLIBC>
 __device__ __forceinline__ double cndf_f64(double x)
 {
     bool neg = x < 0.0;
     double ax = neg ? -x : x;
-    double npx = exp(__dmul_rn(__dmul_rn(-0.5, ax), ax));
+    double npx = exp_ref64<GLIBC>(__dmul_rn(__dmul_rn(-0.5, ax), ax));
     npx = __dmul_rn(npx, 0.39894228040143270286);
     double k1 = __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(0.2316419, ax)));
     double k2 = __dmul_rn(k1, k1);
@@ -277,18 +285,19 @@ __device__ __forceinline__ double cndf_f64(double x)
     return neg ? __dsub_rn(1.0, out) : out;
 }
 
+template <bool GLIBC = false>
 __device__ __forceinline__ double price_f64(double s, double k, double r, double v, double t, int otype)
 {
     double sq = __dsqrt_rn(t);
-    double lg = log(__ddiv_rn(s, k));
+    double lg = log_ref64<GLIBC>(__ddiv_rn(s, k));
     double pw = __dmul_rn(__dmul_rn(v, v), 0.5);
     double d1 = __dadd_rn(__dmul_rn(__dadd_rn(r, pw), t), lg);
     double den = __dmul_rn(v, sq);
     d1 = __ddiv_rn(d1, den);
     double d2 = __dsub_rn(d1, den);
-    double n1 = cndf_f64(d1);
-    double n2 = cndf_f64(d2);
-    double fv = __dmul_rn(k, exp(__dmul_rn(-r, t)));
+    double n1 = cndf_f64<GLIBC>(d1);
+    double n2 = cndf_f64<GLIBC>(d2);
+    double fv = __dmul_rn(k, exp_ref64<GLIBC>(__dmul_rn(-r, t)));
     double call = __dsub_rn(__dmul_rn(s, n1), __dmul_rn(fv, n2));
     double put = __dsub_rn(__dmul_rn(fv, __dsub_rn(1.0, n2)), __dmul_rn(s, __dsub_rn(1.0, n1)));
     return otype == 0 ? call : put;
@@ -298,7 +307,7 @@ __device__ __forceinline__ double price_f64(double s, double k, double r, double
 // loop compact and its register allocation free of libdevice's exp/log/div slow paths.
 __device__ __noinline__ double price_f64_cold(double s, double k, double r, double v, double t, int otype)
 {
-    return price_f64(s, k, r, v, t, otype);
+    return price_f64<false>(s, k, r, v, t, otype);
 }
 
 // fp64 dispatch.  MATH_FAST: bs_math_f64.h (about half the instructions; <= ~2 ulp per building block, measured
@@ -314,7 +323,8 @@ __device__ __forceinline__ double price_f64_any(double s, double k, double r, do
         if (__builtin_expect(ok, 1)) return p;
         return price_f64_cold(s, k, r, v, t, otype);
     }
-    return price_f64(s, k, r, v, t, otype);  // MATH_IEEE and MATH_REFERENCE: with fptype=double nothing is promoted
+    // MATH_IEEE and MATH_REFERENCE: with fptype=double nothing is promoted, the two differ in whose exp/log they call
+    return price_f64<MATH == MATH_REFERENCE>(s, k, r, v, t, otype);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -410,11 +410,73 @@ def test_fp32_reference_mode_err_chk_and_sizes():
     assert errs == 0 and len(bad) == 0   # the reference's own ERR_CHK verdict on this table
 
 
-def test_fp64_reference_mode_is_the_ieee_path():
-    inputs = inputgen_like(100003, seed=4, dtype=np.float64)
-    a, _, _ = gpu_prices(inputs, 8, math=host.MATH_IEEE)
-    b, _, _ = gpu_prices(inputs, 8, math=host.MATH_REFERENCE)
-    assert a.tobytes() == b.tobytes()
+# ---- BS_MATH_REFERENCE, fptype=double: IEEE operation order + glibc's own exp/log (csrc/bs_libm_f64.h) ----------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp64_reference_mode_is_the_reference_output(name):
+    # the prices, written the way the reference writes them ("%.18f", blackscholes.c:936), equal the golden file produced by
+    # the compiled fptype=double reference token for token -- every golden, edge2k included
+    inputs, d = _golden_inputs(name, 8)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=1, math=host.MATH_REFERENCE)
+    ref = _golden_prices(name, "f64")
+    n, toks = oracle_lib.read_prices_text(golden_path(name, "ref_f64.txt"))
+    mine = ["%.18f" % float(x) for x in got]
+    same = sum(a == b for a, b in zip(mine, toks))
+    print("fp64 %-9s reference-mode max|delta| = %.3e, %d of %d output lines identical to the reference's" % (name, np.abs(got - ref).max(), same, n))
+    assert n == len(mine) and same == n   # (the text holds 18 decimals, not the doubles' bits: those are compared with the oracle below)
+    assert got.tobytes() == oracle_prices(inputs, 8).tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 257, 65537, 1000003])
+def test_fp64_reference_mode_bit_identical_to_oracle_sizes(n):
+    inputs = inputgen_like(n, seed=n + 300, dtype=np.float64)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=2, math=host.MATH_REFERENCE)
+    ref = oracle_prices(inputs, 8)
+    assert got.tobytes() == ref.tobytes(), "n=%d: %d of %d prices differ, max |delta| %.3e" % (n, int((got != ref).sum()), n, np.abs(got - ref).max())
+
+
+def test_fp64_reference_mode_native_10m_and_wide_operands():
+    # 10M random options of the inputgen range, then 2M with operands far outside it (spot/strike over twelve decades,
+    # volatilities and maturities that drive |d| beyond 38, where exp(-d^2/2) is subnormal or zero, and rates that push
+    # exp(-r t) through glibc's |x| >= 512 branch): every price equal to the oracle's, NaN and inf included
+    n = 10_000_000
+    inputs = inputgen_like(n, seed=81, dtype=np.float64)
+    got, _, _ = gpu_prices(inputs, 8, num_runs=1, math=host.MATH_REFERENCE, with_dgrefval=False)
+    ref = oracle_prices(inputs, 8)
+    exact = float(np.mean(got == ref))
+    print("fp64 reference mode, 10M random inputgen-range options: bit-identical %.4f%%, max|delta| = %.3e" % (100 * exact, np.abs(got - ref).max()))
+    assert got.tobytes() == ref.tobytes()
+    rng = np.random.default_rng(5)
+    m = 2_000_000
+    s = 10.0 ** rng.uniform(-6, 6, m)
+    k = s * 10.0 ** rng.uniform(-3, 3, m)
+    r = rng.choice([0.0, 0.05, -0.05, 3.0, 600.0, -600.0, 800.0], m, p=[0.1, 0.5, 0.1, 0.1, 0.1, 0.05, 0.05])
+    v = 10.0 ** rng.uniform(-4, 1, m)
+    t = 10.0 ** rng.uniform(-4, 1.5, m)
+    o = rng.integers(0, 2, m).astype(np.int32)
+    wide = (s, k, r, v, t, o)
+    got, _, _ = gpu_prices(wide, 8, num_runs=1, math=host.MATH_REFERENCE, with_dgrefval=False)
+    ref = oracle_prices(wide, 8)
+    both_nan = np.isnan(got) & np.isnan(ref)
+    same = both_nan | (got.view(np.uint64) == ref.view(np.uint64))
+    print("fp64 reference mode, 2M wide-range options: %d differ; %d NaN, %d inf, %d zero or subnormal prices in the reference output"
+          % (int((~same).sum()), int(np.isnan(ref).sum()), int(np.isinf(ref).sum()), int((np.abs(ref) < 2.3e-308).sum())))
+    assert same.all()
+
+
+def test_fp64_reference_mode_degenerate_rows_and_err_chk():
+    s = np.array([100.0, 90.0, 100.0, 100.0, 100.0, 1e-310, 100.0, 100.0, 100.0, 100.0, 0.0, -5.0])
+    k = np.array([90.0, 100.0, 100.0, 90.0, 110.0, 100.0, 1e308, 90.0, 90.0, 90.0, 100.0, 100.0])
+    r = np.array([0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.05, -800.0, 800.0, 0.05, 0.05])
+    v = np.array([0.2, 0.2, 0.2, 0.0, 0.0, 0.2, 0.2, 1e-160, 0.2, 0.2, 0.2, 0.2])
+    t = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    for o in (0, 1):
+        inputs = (s, k, r, v, t, np.full(len(s), o, np.int32))
+        ref = oracle_prices(inputs, 8)
+        got, _, _ = gpu_prices(inputs, 8, math=host.MATH_REFERENCE)
+        assert ((np.isnan(got) & np.isnan(ref)) | (got.view(np.uint64) == ref.view(np.uint64))).all(), (o, got, ref)
+    inputs, d = _golden_inputs("table1k", 8)
+    _, errs, bad = gpu_prices(inputs, 8, num_runs=2, dgrefval=d["dgrefval"], err_chk=True, math=host.MATH_REFERENCE)
+    assert errs == 0 and len(bad) == 0   # the fptype=double reference's own ERR_CHK verdict on this table
 
 
 # ---- the CAF Map's entry: AoS DataCont records (blackscholes.c:482-570) -----------------------------------------
@@ -604,6 +666,21 @@ def test_driver_binary_reference_math_writes_the_reference_file(name, tmp_path):
     cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu"), "1", golden_path(name, "in.txt"), out], capture_output=True, text=True,
                         env=dict(os.environ, BS_GPU_MATH="bogus"))
     assert cp.returncode == 1 and "BS_GPU_MATH" in cp.stdout
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_driver_binary_fp64_reference_math_writes_the_reference_file(name, tmp_path):
+    # the same for the fptype=double build: byte for byte the file the reference's fp64 CPU build wrote, and its ERR_CHK lines
+    out = str(tmp_path / "prices.txt")
+    cp = subprocess.run([os.path.join(BIN, "blackscholes_gpu_fp64_errchk"), "1", golden_path(name, "in.txt"), out], capture_output=True, text=True,
+                        env=dict(os.environ, BS_GPU_MATH="reference"))
+    assert cp.returncode == 0, cp.stdout + cp.stderr
+    assert open(out, "rb").read() == open(golden_path(name, "ref_f64.txt"), "rb").read()
+    gold = json.load(open(golden_path(name, "errchk.json")))["f64"]
+    lines = cp.stdout.splitlines()
+    assert gold["num_errors_line"] in lines
+    mine = [l for l in lines if l.startswith("Error on ")]
+    assert sorted(set(mine)) == sorted(set(gold["errors_one_run"])) and len(mine) == 100 * len(gold["errors_one_run"])
 
 
 def test_driver_binary_err_chk_and_usage(tmp_path):

@@ -12,7 +12,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from p3arsec_b200 import host  # noqa: E402
 
-M = {"fast": host.MATH_FAST, "ieee": host.MATH_IEEE}
+M = {"fast": host.MATH_FAST, "ieee": host.MATH_IEEE, "reference": host.MATH_REFERENCE}
 # (fp_bytes, math, unroll, threads, blocks_per_sm, variant)   variant: 1 = pipelined loads, 2 = traffic probe
 CONFIGS = {
     "fp32": [(4, "fast", 1, 256, 4, 0), (4, "fast", 1, 128, 8, 0), (4, "fast", 2, 256, 0, 0), (4, "fast", 1, 256, 0, 1), (4, "fast", 1, 256, 3, 1),
@@ -28,6 +28,7 @@ CONFIGS = {
     "fp64r2": [(8, "fast", 1, 256, 0, 1), (8, "fast", 1, 224, 0, 1), (8, "fast", 1, 192, 0, 1), (8, "fast", 1, 160, 0, 1), (8, "fast", 1, 128, 0, 1),
                (8, "fast", 1, 96, 0, 1), (8, "fast", 1, 64, 0, 1), (8, "fast", 1, 256, 0, 0), (8, "fast", 1, 192, 0, 0), (8, "fast", 1, 128, 0, 0),
                (8, "fast", 2, 128, 0, 0), (8, "fast", 2, 128, 0, 1), (8, "fast", 2, 256, 0, 1), (8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2)],
+    "fp64ref": [(8, "reference", 1, 256, 0, 0), (8, "ieee", 1, 256, 0, 0), (8, "ieee", 1, 256, 0, 1), (4, "reference", 1, 256, 0, 0), (4, "ieee", 1, 256, 0, 0)],
     "fp64tma2": [(8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 68), (8, "fast", 1, 256, 0, 36), (8, "fast", 1, 256, 0, 1), (8, "fast", 1, 256, 0, 6),
                  (8, "fast", 1, 256, 0, 70), (8, "fast", 1, 256, 0, 2)],
     "fp64tma": [(8, "fast", 1, 256, 0, 1), (8, "fast", 1, 256, 0, 4), (8, "fast", 1, 256, 0, 36), (8, "fast", 1, 256, 0, 2), (8, "fast", 2, 256, 0, 2),
