@@ -605,9 +605,12 @@ void do_price(bs_gpu_ctx *c, Shard &s)
         if (S > 1 && R >= 1 && !(c->flags & BS_GPU_FLAG_NO_SUBSHARDS)) { do_price_subshards(c, s, S); return; }
     }
 
-    // chunk boundaries: multiples of 1024 options keep every stream 16-byte aligned
+    // chunk boundaries: multiples of 1024 options keep every stream 16-byte aligned.  Shards whose copies are bound by
+    // latency, not by bandwidth (under 4 MiB of streams: simsmall is 112 KB), go in ONE chunk: eight chunks of six
+    // streams each would be 48 copies of a few KB and a dozen extra launches around 100 launches of a microsecond each.
+    const int NCH = s.count * (5 * elem_bytes(c, BS_BUF_SPTPRICE) + 4 + elem_bytes(c, BS_BUF_PRICES)) < ((size_t)4 << 20) ? 1 : PIPE_CHUNKS;
     size_t lo[PIPE_CHUNKS + 1];
-    const size_t per = ((s.count + PIPE_CHUNKS - 1) / PIPE_CHUNKS + 1023) & ~(size_t)1023;
+    const size_t per = ((s.count + NCH - 1) / NCH + 1023) & ~(size_t)1023;
     for (int k = 0; k <= PIPE_CHUNKS; k++) lo[k] = std::min(s.count, per * (size_t)k);
     const size_t pe = elem_bytes(c, BS_BUF_PRICES);
 
@@ -617,7 +620,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
 
     // ---- inputs: chunked H2D on the copy stream
     if (what) {
-        for (int k = 0; k < PIPE_CHUNKS; k++) {
+        for (int k = 0; k < NCH; k++) {
             const size_t n = lo[k + 1] - lo[k];
             if (n) {
                 if (what & UP_INPUTS)
@@ -648,7 +651,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     };
     if (R >= 1 && what) {  // run 0 follows the input chunks (it is also the last run when R == 1)
         const bool last = (R == 1);
-        for (int k = 0; k < PIPE_CHUNKS; k++) {
+        for (int k = 0; k < NCH; k++) {
             SH_CUDA(cudaStreamWaitEvent(s.stream, s.ev_in[k], 0));
             SH_CUDA(mark_k0());
             SH_CUDA(launch_map_range(c, s, chk, chk && last, lo[k], lo[k + 1] - lo[k]));
@@ -668,7 +671,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     }
     bool out_marked = (R == 1 && what);
     if (done < R) {  // the last run, chunk by chunk, each chunk's prices leaving as soon as they exist
-        for (int k = 0; k < PIPE_CHUNKS; k++) {
+        for (int k = 0; k < NCH; k++) {
             SH_CUDA(launch_map_range(c, s, chk, chk, lo[k], lo[k + 1] - lo[k]));
             SH_CUDA(cudaEventRecord(s.ev_out[k], s.stream));
         }
@@ -678,7 +681,7 @@ void do_price(bs_gpu_ctx *c, Shard &s)
     SH_CUDA(cudaEventRecord(s.ev_k1, s.stream));
 
     // ---- prices: chunked D2H on the copy stream
-    for (int k = 0; k < PIPE_CHUNKS; k++) {
+    for (int k = 0; k < NCH; k++) {
         const size_t n = lo[k + 1] - lo[k];
         if (out_marked) SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_out[k], 0));
         else if (k == 0) SH_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_k1, 0));
