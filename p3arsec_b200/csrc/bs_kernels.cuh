@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
 
     // the fp64 fast math reads two 64-entry tables (bs_math_f64.h) from shared memory; other variants carry 8 bytes
     enum { USE_TAB = (sizeof(FP) == 8 && MATH == MATH_FAST) ? 1 : 0 };
-    __shared__ double s_tab[USE_TAB ? bsm::BS_F64_TAB_DOUBLES : 1];
+    __shared__ __align__(16) unsigned char s_tab_raw[USE_TAB ? bsm::BS_F64_TAB_DOUBLES * sizeof(double) + bsm::BS_F64_TAB_PAD : 16];
+    double *s_tab = USE_TAB ? bsm::place_tables(s_tab_raw) : reinterpret_cast<double *>(s_tab_raw);
     if (USE_TAB) {
         bsm::BS_F64_FILL_TABLES(s_tab, (int)threadIdx.x, (int)blockDim.x);
         __syncthreads();
@@ -604,7 +605,7 @@ template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_stage
 template <typename FP, int SHAPE> __host__ __device__ constexpr size_t tma_smem_bytes()
 {
     return tma_stage_bytes<FP, SHAPE>() * TmaCfg<FP, SHAPE>::STAGES + 2 * TmaCfg<FP, SHAPE>::STAGES * sizeof(uint64_t) + 128 +
-           ((sizeof(FP) == 8) ? bsm::BS_F64_TAB_DOUBLES * sizeof(double) : 0);
+           ((sizeof(FP) == 8) ? bsm::BS_F64_TAB_DOUBLES * sizeof(double) + bsm::BS_F64_TAB_PAD : 0);
 }
 template <typename FP, int SHAPE> __host__ __device__ constexpr int tma_threads() { return TmaCfg<FP, SHAPE>::CONSUMERS + 32; }
 
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(TmaCfg<FP, SHAPE>::CONSUMERS + 32, 1) bs_map_t
     unsigned char *stage_base = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGE_BYTES * STAGES);
     uint64_t *empty = full + STAGES;
-    double *s_tab = reinterpret_cast<double *>(empty + STAGES + 2);
     enum { USE_TAB = (sizeof(FP) == 8 && MATH == MATH_FAST) ? 1 : 0 };
+    double *s_tab = USE_TAB ? bsm::place_tables(empty + STAGES + 2) : reinterpret_cast<double *>(empty + STAGES + 2);
     (void)ec;
 
     const size_t tiles = n / TILE;

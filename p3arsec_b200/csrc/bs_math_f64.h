@@ -104,7 +104,7 @@ BS_HD double rsqrt_f64(double t)
     double y = seed_rsqrt(t);
     double a = t * y;
     double e = fma(-a, y, 1.0);
-    double c = fma(0.375, e, 0.5);
+    double c = fma(kd(K_RSQ_C2), e, 0.5);     // 0.375 from the constant bank: DFMA takes one immediate, and 0.5 is it
     double ye = y * e;
     return fma(ye, c, y);
 }
@@ -123,12 +123,27 @@ BS_HD void fill_tables(double *tab, int first, int step)
 // (- ln2 for i >= LOG256_SPLIT)}.  Finer intervals buy shorter polynomials -- degree 4 instead of 5 for exp (|r| <= ln2/512:
 // r^5/120 < 4e-17), degree 5 instead of 7 for log (|r| < 2^-9: r^6/6 < 1e-17) -- i.e. four FP64 instructions less per option
 // at the same accuracy; the kernel is FP64-issue- and, sustained, power-bound.
-enum { TAB256_EXP = 0, TAB256_LOG = 256, TAB256_DOUBLES = 256 + 512 };
+// Layout: [0,512) the 256 log pairs (4 KB), [512,768) 2^(j/256) (2 KB).  On the device the block must start on a 4 KB
+// boundary of shared memory (TAB256_ALIGN; both kernels place it so with place_tables256): each sub-table is then aligned to
+// its own size and an entry's address is `base | index bits` -- one LOP3 on the bits as they come out of the argument,
+// instead of mask, shift and add (BS_F64_TAB_OR; 7 integer instructions less per option of ~95).
+enum { TAB256_LOG = 0, TAB256_EXP = 512, TAB256_DOUBLES = 512 + 256, TAB256_ALIGN = 4096 };
+#ifndef BS_F64_TAB_OR
+#define BS_F64_TAB_OR 1
+#endif
 
+// With BS_F64_TAB_OR the device's copy of entry j of the exp table is 2^(j/256) with j * 2^12 subtracted from its high
+// word: exp256_core_f64 then adds n * 2^12 = (256 k + j) * 2^12 to that word, which puts k into the exponent field and takes
+// the bias out again -- the index bits need not be masked off n first.
 BS_HD void fill_tables256(double *tab, int first, int step)
 {
-    for (int i = first; i < TAB256_DOUBLES; i += step)
-        tab[i] = from_bits(i < TAB256_LOG ? EXP2_256_BITS[i] : LOG256_RC_LC_BITS[(i - TAB256_LOG) >> 1][(i - TAB256_LOG) & 1]);
+    for (int i = first; i < TAB256_DOUBLES; i += step) {
+        uint64_t b = i < TAB256_EXP ? LOG256_RC_LC_BITS[i >> 1][i & 1] : EXP2_256_BITS[i - TAB256_EXP];
+#if defined(__CUDA_ARCH__) && BS_F64_TAB_OR
+        if (i >= TAB256_EXP) b -= (uint64_t)(i - TAB256_EXP) << 44;
+#endif
+        tab[i] = from_bits(b);
+    }
 }
 
 // exp(x) for x <= ~700 (the Map only needs x <= 0): exact zero below -708 (no subnormal results).
@@ -220,18 +235,40 @@ BS_HD double exp256_core_f64(double x, const double *tab)
     double q = fma(kd(K_EXP_C4), r, kd(K_EXP_C3));
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);         // r + r^2/2 + r^3/6 + r^4/24
+#if defined(__CUDA_ARCH__) && BS_F64_TAB_OR
+    // biased entry j at (base + 4 KB) | (j << 3); its high word + n * 2^12 is the high word of 2^k 2^(j/256) (fill_tables256):
+    // one LOP3 for the address, one IMAD for the scaling, and the scaled T goes through the final FMA
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab) + TAB256_EXP * 8;
+    int lo, hi;
+    asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(base | (((uint32_t)n << 3) & 0x7f8u)));
+    asm("mad.lo.s32 %0, %1, 4096, %0;" : "+r"(hi) : "r"(n));    // in place: the loaded pair becomes T
+    const double T = __hiloint2double(hi, lo);                   // 2^k 2^(j/256), normal for |x| < 700
+    return fma(T, em1, T);
+#else
     const double T = tab[TAB256_EXP + (n & 255)];
     return scale_by_pow2(fma(T, em1, T), n >> 8);
+#endif
 }
 
 // log(x) for normal x > 0 from the 256-entry table: 9 FP64 instructions.
 BS_HD double log256_f64(double x, const double *tab)
 {
     const uint64_t b = to_bits(x);
+    const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+#if defined(__CUDA_ARCH__) && BS_F64_TAB_OR
+    // pair i at base | (i << 4), i = the top 8 mantissa bits = bits 12..19 of the high word: (hi >> 8) & 0xff0
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab) + TAB256_LOG * 8;
+    const uint32_t hw = (uint32_t)(b >> 32);
+    const uint32_t addr = base | ((hw >> 8) & 0xff0u);
+    double rc, lc;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lc) : "r"(addr));
+    // e + 1 from LOG256_SPLIT on: adding (256 - SPLIT) to the index bits carries into the exponent field exactly then
+    const int e = (int)((hw + ((256u - LOG256_SPLIT) << 12)) >> 20) - 1023;
+#else
     const int i = (int)(b >> 44) & 255;          // top 8 mantissa bits: m in [1 + i/256, 1 + (i+1)/256)
     const int e = (int)(b >> 52) - 1023 + (i >= LOG256_SPLIT ? 1 : 0);
-    const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
     const double rc = tab[TAB256_LOG + 2 * i], lc = tab[TAB256_LOG + 2 * i + 1];
+#endif
     const double r = fma(m, rc, -1.0);           // |r| < 2^-9
     double q = fma(kd(K_LOG_C5), r, -0.25);      // r - r^2/2 + r^3/3 - r^4/4 + r^5/5
     q = fma(q, r, kd(K_LOG_C3));
@@ -250,13 +287,39 @@ BS_HD double log256_f64(double x, const double *tab)
 #define BS_F64_LOG log_f64
 #define BS_F64_EXP exp_core_f64
 #define BS_F64_FILL_TABLES fill_tables
-enum { BS_F64_TAB_DOUBLES = TAB_DOUBLES };
+enum { BS_F64_TAB_DOUBLES = TAB_DOUBLES, BS_F64_TAB_PAD = 0 };
 #else
 #define BS_F64_LOG log256_f64
 #define BS_F64_EXP exp256_core_f64
 #define BS_F64_FILL_TABLES fill_tables256
-enum { BS_F64_TAB_DOUBLES = TAB256_DOUBLES };
+enum { BS_F64_TAB_DOUBLES = TAB256_DOUBLES, BS_F64_TAB_PAD = BS_F64_TAB_OR ? TAB256_ALIGN : 0 };
 #endif
+// Where the kernel's table block goes inside `raw` (BS_F64_TAB_DOUBLES * 8 + BS_F64_TAB_PAD bytes of shared memory): the
+// first address whose offset in the shared window is a multiple of the alignment the `base | index` addressing needs.
+#if defined(__CUDACC__)
+__device__ __forceinline__ double *place_tables(void *raw)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
+    return reinterpret_cast<double *>(static_cast<unsigned char *>(raw) + (BS_F64_TAB_PAD ? ((0u - a) & (uint32_t)(BS_F64_TAB_PAD - 1)) : 0u));
+}
+#endif
+
+// p with its sign flipped unless the sign bit of x is set: one LOP3 on the high word (p_hi ^ (~x & SIGN)).
+BS_HD double flip_sign_unless(double p, uint32_t x)
+{
+    return from_bits(to_bits(p) ^ ((uint64_t)(~x & 0x80000000u) << 32));
+}
+// a for x >= 0, (+)0 for x < 0.  On the device only the high word is selected: what remains for x < 0 is a denormal below
+// 2^-1042 instead of an exact zero -- it enters the price through one addition, 300 orders of magnitude below the
+// tolerance, and saves the second FSEL of a 64-bit select (the kernel is bound by instruction issue).
+BS_HD double zero_if_negative(double a, int x)
+{
+#if defined(__CUDA_ARCH__) && BS_F64_TAB_OR
+    return __hiloint2double(x < 0 ? 0 : __double2hiint(a), __double2loint(a));
+#else
+    return x < 0 ? 0.0 : a;
+#endif
+}
 
 // poly(k) with k = 1/(1 + 0.2316419|d|): the CNDF tail 1 - N(|d|) is exp(-d^2/2) k poly(k) / sqrt(2 pi); the constants
 // of CNDF (blackscholes.c:126,:156,:164-170) are pre-multiplied by 1/sqrt(2 pi).
@@ -305,17 +368,18 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     const double a1 = fma(fabs(d1), kd(K_CNDF_C), 1.0), a2 = fma(fabs(d2), kd(K_CNDF_C), 1.0);
     const double a12 = a1 * a2;
     const double rab = rcp_f64(a12);             // one reciprocal serves both CNDF arguments   :156-158
-    const double g = s * BS_F64_EXP((-0.5 * d1) * d1, tab);  // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
+    const double q1 = (-0.5 * d1) * d1;          // -d1^2/2
+    const double g = s * BS_F64_EXP(q1, tab);    // s exp(-d1^2/2): s n(d1) = fv n(d2), up to 1/sqrt(2 pi)
     const double P1 = cndf_poly_f64(rab * a2), P2 = cndf_poly_f64(rab * a1);
     // N(x) = tail w for x < 0 and 1 - w otherwise; a put needs N(-x): the tail itself is wanted when sign(d) != put.   :249-255
-    const uint64_t SIGN = 0x8000000000000000ull;
-    const uint64_t putm = otype != 0 ? SIGN : 0ull;
-    const uint64_t m1 = (to_bits(d1) ^ putm) & SIGN, m2 = (to_bits(d2) ^ putm) & SIGN;  // SIGN: the tail itself
-    const double t1 = from_bits(to_bits(P1) ^ m1 ^ SIGN);   // +P1 for the tail, -P1 for 1 - tail
-    const double t2 = from_bits(to_bits(P2) ^ m2 ^ SIGN);
-    const uint64_t all1 = (uint64_t)((int64_t)m1 >> 63), all2 = (uint64_t)((int64_t)m2 >> 63);
-    const double bs = from_bits(to_bits(s) & ~all1);        // s when N1 = 1 - w1, else 0
-    const double bf = from_bits(to_bits(fv) & ~all2);       // fv when N2 = 1 - w2, else 0
+    // Sign bit of x_j = high word of d_j XOR put flag: set <=> the tail itself is wanted.
+    const uint32_t SIGN = 0x80000000u;
+    const uint32_t puth = otype != 0 ? SIGN : 0u;
+    const uint32_t x1 = (uint32_t)(to_bits(d1) >> 32) ^ puth, x2 = (uint32_t)(to_bits(d2) >> 32) ^ puth;
+    const double t1 = flip_sign_unless(P1, x1);             // +P1 for the tail, -P1 for 1 - tail
+    const double t2 = flip_sign_unless(P2, x2);
+    const double bs = zero_if_negative(s, (int)x1);         // s when N1 = 1 - w1, else 0
+    const double bf = zero_if_negative(fv, (int)x2);        // fv when N2 = 1 - w2, else 0
     const double c = fma(g, t1 - t2, bs - bf);
     // Domain of the blocks above (integer range checks on the high words; everything else -- t = 0, v = 0, s <= 0,
     // NaN, inf, denormals, overflow -- is left to the IEEE-order path, which reproduces the reference's inf/NaN results):
@@ -323,14 +387,17 @@ BS_HD double price_f64_fast(double s, double k, double r, double v, double t, in
     //              block cannot invert -- zero, denormal, >= 2^1022, inf, NaN -- yields s/k = 0, inf or NaN);
     //   |d1| < 37: exp(-d1^2/2) has not underflowed, so expressing the second tail through it loses nothing
     //              (inside the inputgen range |d1| <= 32);
-    //   a1 a2 = (1 + c|d1|)(1 + c|d2|) finite: the shared reciprocal is not 0 * inf (v below ~1e-154);
+    //   a1 a2 = (1 + c|d1|)(1 + c|d2|) finite: the shared reciprocal is not 0 * inf -- implied by the two above;
     //   |r t| < 512: the exponent arithmetic of exp_core_f64 cannot wrap (the reference returns inf / NaN there).
+    // (a1 a2 needs no check of its own: |d1| < 37 and xDen = sqrt(v^2 t) < 2^128 bound it by 2^130.)
+    // The three range checks share one compare: x - LO < SPAN for all three <=> the OR of the differences is < SPAN
+    // (SPAN is a power of two).  |d1| < 37 is tested on the exponential's argument q = -d1^2/2, whose sign bit is always
+    // set: high word - 0x80000000 < high word of 684.5 (a NaN fails with either sign); |r t| < 512 on the high word
+    // shifted left by one (drops the sign).
     const uint32_t LO = 0x30000000u, SPAN = 0x20000000u;
-    const uint32_t hi_d1 = (uint32_t)(to_bits(d1) >> 32) & 0x7fffffffu, hi_rt = (uint32_t)(to_bits(rt) >> 32) & 0x7fffffffu;
-    *ok = ((uint32_t)(to_bits(v) >> 32) - LO < SPAN) && ((uint32_t)(to_bits(z) >> 32) - LO < SPAN) &&
-          ((uint32_t)(to_bits(sk) >> 32) - LO < SPAN) && (hi_d1 < 0x40428000u) && ((uint32_t)(to_bits(a12) >> 32) < 0x6ff00000u) &&
-          (hi_rt < 0x40800000u);
-    return from_bits(to_bits(c) ^ putm);   // put: fv N(-d2) - s N(-d1) = -(s N(-d1) - fv N(-d2))
+    const uint32_t span3 = ((uint32_t)(to_bits(v) >> 32) - LO) | ((uint32_t)(to_bits(z) >> 32) - LO) | ((uint32_t)(to_bits(sk) >> 32) - LO);
+    *ok = (span3 < SPAN) && ((uint32_t)(to_bits(q1) >> 32) - 0x80000000u < 0x40856400u) && ((uint32_t)(to_bits(rt) >> 32) << 1 < 0x81000000u);
+    return from_bits(to_bits(c) ^ ((uint64_t)puth << 32));   // put: fv N(-d2) - s N(-d1) = -(s N(-d1) - fv N(-d2))
 }
 
 }  // namespace bsm

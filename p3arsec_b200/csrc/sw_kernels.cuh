@@ -57,13 +57,11 @@ namespace swk {
 
 #if defined(__CUDACC__)
 SW_HD int ffs32(uint32_t v) { return __ffs((int)v); }
-SW_HD uint32_t umax32(uint32_t a, uint32_t b) { return max(a, b); }
 SW_HD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 SW_HD double add_rn(double a, double b) { return __dadd_rn(a, b); }
 SW_HD double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 #else
 SW_HD int ffs32(uint32_t v) { return __builtin_ffs((int)v); }
-SW_HD uint32_t umax32(uint32_t a, uint32_t b) { return std::max(a, b); }
 SW_HD double mul_rn(double a, double b) { return a * b; }  // no contraction: the host build uses -ffp-contract=off
 SW_HD double add_rn(double a, double b) { return a + b; }
 SW_HD double div_rn(double a, double b) { return a / b; }
@@ -80,6 +78,8 @@ struct SwParams {
     double driftdt[MAXN];        // pdTotalDrift[l] * ddelt (HSB:148 + the product inside HJM_SimPath_Forward_Blocking)
     double fac[MAXF][MAXN];      // ppdFactors
     double pay[MAXN];            // pdSwapPayoffs, zero beyond iSwapVectorLength (HSB:132-140)
+    double xd_path[MAXN];        // -(cumulative drift of path entry [j][0]) * ddelt       (fast kernels, see path_and_payoff)
+    double xd_swap[MAXN];        // -(cumulative drift of path entry [start][i]) * swap_ddelt
     double ddelt;                // HSB:48
     double sqrt_ddelt;           // HJM_SimPath_Forward_Blocking
     double swap_ddelt;           // dSwapVectorYears / iSwapVectorLength (Discount_Factors_Blocking at HSB:184)
@@ -176,11 +176,24 @@ SW_HD_NOINLINE double exp_slow(double x) { return exp(x); }
 // plain 64-entry table in shared memory serves a half-warp's 64-bit loads in 2-4 wavefronts (16 bank pairs, 16 lanes
 // with unrelated j).  REP = 16 copies interleaved [j][lane & 15] give every lane of a half-warp its own bank pair
 // whatever j is: always one wavefront (8 KB per CTA).  REP = 1 is the plain table (host checker, generic fallback).
+// scaled(n) = 2^(n >> 6) 2^((n & 63)/64) for n = round(x 64/ln2).  The replicated copy is BIASED (load_exp_replicated): entry
+// j carries j * 2^14 less in its high word, so that adding n * 2^14 = (64 k + j) * 2^14 puts k into the exponent field and
+// takes the bias out again -- one IMAD instead of shift, mask and add (twenty exponentials per trial).
 template <int REP_SHIFT>
 struct ExpTab {
     const double *t;
     int lane;
     SW_HD double at(int j) const { return t[(j << REP_SHIFT) + lane]; }
+    SW_HD double scaled(int n) const
+    {
+#if defined(__CUDA_ARCH__)
+        if (REP_SHIFT) {
+            const double tb = at(n & 63);
+            return __hiloint2double(n * 16384 + __double2hiint(tb), __double2loint(tb));
+        }
+#endif
+        return bsm::scale_by_pow2(at(n & 63), n >> 6);
+    }
 };
 constexpr int EXP_REP_SHIFT = 4, EXP_REP_DOUBLES = 64 << EXP_REP_SHIFT;
 // The same for log_f64's {1/c, log c} pairs, read as one 128-bit load: a quarter-warp (8 lanes) per wavefront, so 8 copies
@@ -216,19 +229,24 @@ SW_HD double exp_core(double x, const ET &et)
     q = fma(q, r, kd(K_EXP_C3));
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
-    const double T = et.at(n & 63);
-    return scale_by_pow2(fma(T, em1, T), n >> 6);
+    const double T = et.scaled(n);   // 2^k 2^(j/64): normal for |x| < 700, so scaling T first changes no bit of the result
+    return fma(T, em1, T);
 }
 // |x| >= 700, inf or NaN <=> (high word of x, sign cleared) >= EXP_HI_LIMIT.  The fast kernel evaluates every
 // exponential with exp_core, branch-free, and only tracks the largest such high word of the trial (LOP3 + VIMNMX on the
 // integer pipes); a trial that exceeded the limit is redone by generic_trial().
+// `worst` accumulates the high words with OR (a three-input LOP3 takes two exponentials at a time; a running maximum of the
+// sign-cleared words cost a LOP3 and a VIMNMX each): the OR is >= every word, and words below 0x40000000 (|x| < 2, i.e.
+// every rate below 200 % a year) cannot OR up to the limit, so the test is exact for them and conservative above -- a
+// trial sent to generic_trial() without need is still priced correctly.
 constexpr uint32_t EXP_HI_LIMIT = 0x4085E000u;
 template <class ET>
 SW_HD double exp_tracked(double x, const ET &et, uint32_t &worst)
 {
-    worst = umax32(worst, (uint32_t)(bsm::to_bits(x) >> 32) & 0x7fffffffu);
+    worst |= (uint32_t)(bsm::to_bits(x) >> 32);
     return exp_core(x, et);
 }
+SW_HD bool exp_range_left(uint32_t worst) { return (worst & 0x7fffffffu) >= EXP_HI_LIMIT; }
 
 // CumNormalInv takes its central branch iff fabs(u - 0.5) < 0.42 with u = s * 4.656612875e-10 (s the 31-bit draw).
 // Both roundings are monotone in s, so the test is an integer range check: central <=> S_LO <= s <= S_HI
@@ -287,7 +305,10 @@ SW_HD void load_tables(double *__restrict__ smem_tail_then_tab, const double *__
 }
 SW_HD void load_exp_replicated(double *__restrict__ xexp, const double *__restrict__ g, int tid)
 {
-    for (int i = tid; i < EXP_REP_DOUBLES; i += THREADS) xexp[i] = g[swt::TAIL_DOUBLES + bsm::TAB_EXP + (i >> EXP_REP_SHIFT)];
+    for (int i = tid; i < EXP_REP_DOUBLES; i += THREADS) {  // biased by j * 2^14 in the high word (ExpTab::scaled)
+        const int j = i >> EXP_REP_SHIFT;
+        xexp[i] = bsm::from_bits(bsm::to_bits(g[swt::TAIL_DOUBLES + bsm::TAB_EXP + j]) - ((uint64_t)j << 46));
+    }
 }
 SW_HD void load_log_replicated(double *__restrict__ xlog, const double *__restrict__ g, int tid)
 {
@@ -371,6 +392,8 @@ struct FastShared {
     double4 fd[FN - 1];        // per maturity l: {fac0, fac1, fac2} * sqrt_ddelt and pdTotalDrift[l] * ddelt (two LDS.128)
     double fwd[FN];
     double pay[FN];
+    double xdp[FN];            // SwParams::xd_path
+    double xds[FN];            // SwParams::xd_swap
     double red[2][THREADS / 32];
     double xexp[EXP_REP_DOUBLES];  // 2^(j/64) replicated [j][lane & 15]: conflict-free whatever the lanes' j (ExpTab)
     double xlog[LOG_REP_DOUBLES];  // {1/c, log c} replicated [i][lane & 7] (LogTabRep)
@@ -522,6 +545,11 @@ SW_HD void normals(const LT &tab, const double *__restrict__ tailtab, double *__
 // ---- phase B --------------------------------------------------------------------------------------------------------------
 // The forward-rate path row by row in registers (HJM_SimPath_Forward_Blocking), column 0 feeding the payoff discount
 // factor (HSB:167-172), row `start` feeding the swap leg (HSB:179-195); returns the discounted payoff (HSB:198).
+// The rows are kept WITHOUT their drift: entry [j][l] of the reference's path is R_j[l] + cd_j[l] with the shocks-only recursion
+// R_j[l] = R_{j-1}[l+1] + sqrt(ddelt) sum_i fac_i[l] z_{j,i} (three FMAs on the previous row's entry, no addition of its own)
+// and the cumulative drift cd_j[l] = cd_{j-1}[l+1] + pdTotalDrift[l] ddelt, which is the same for every trial.  The path is
+// only ever read as an argument of exp(-rate * dt) -- column 0 of every row and the start row -- so prepare() folds cd into
+// those twenty arguments (xd_path, xd_swap) and the multiplication -rate * dt becomes an FMA: 55 FP64 additions less per trial.
 // START >= 0: the swap start index as a compile-time constant -- the row snapshot is then a register renaming and the
 // whole phase is one basic block; START < 0: taken from start_rt.  Every exponential is evaluated branch-free; `worst`
 // remembers whether one of them left the fast range.
@@ -543,7 +571,8 @@ SW_HD double path_and_payoff(const SRC &sh, const ET &tab, const double *__restr
 #pragma unroll
     for (int j = 1; j <= FN - 1; ++j) {
         if (!LEAN || j <= steps) {
-            run *= exp_tracked(-row[0] * ddelt, tab, worst);  // Discount_Factors_Blocking: DF[j] = DF[j-1] e_{j-1}
+            // Discount_Factors_Blocking: DF[j] = DF[j-1] exp(-(rate of row j-1, column 0) * ddelt)
+            run *= exp_tracked(fma(-row[0], ddelt, sh.xdp[j - 1]), tab, worst);
             const double z0 = z[(FF * (j - 1) + 0) * THREADS + tid];
             const double z1 = z[(FF * (j - 1) + 1) * THREADS + tid];
             const double z2 = z[(FF * (j - 1) + 2) * THREADS + tid];
@@ -554,10 +583,9 @@ SW_HD double path_and_payoff(const SRC &sh, const ET &tab, const double *__restr
             for (int l = 0; l <= FN - 1 - j; ++l) {
                 if (!LEAN || l <= need) {
                     const double4 c = sh.fd[l];
-                    double shock = fma(c.x, z0, c.w);
-                    shock = fma(c.y, z1, shock);
-                    shock = fma(c.z, z2, shock);
-                    row[l] = row[l + 1] + shock;
+                    double v = fma(c.x, z0, row[l + 1]);
+                    v = fma(c.y, z1, v);
+                    row[l] = fma(c.z, z2, v);
                 }
             }
             row[FN - j] = 0.0;  // the reference's path matrix is zero beyond the triangle
@@ -575,7 +603,7 @@ SW_HD double path_and_payoff(const SRC &sh, const ET &tab, const double *__restr
 #pragma unroll
     for (int i = 1; i <= FN - 1; ++i) {
         if (!LEAN || i <= swap_end) {
-            df *= exp_tracked(-srow[i - 1] * swap_ddelt, tab, worst);
+            df *= exp_tracked(fma(-srow[i - 1], swap_ddelt, sh.xds[i - 1]), tab, worst);
             fixed = fma(sh.pay[i], df, fixed);
         }
     }
@@ -617,6 +645,8 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             if (tid < FN) {
                 sh.fwd[tid] = P.fwd[tid];
                 sh.pay[tid] = P.pay[tid];
+                sh.xdp[tid] = P.xd_path[tid];
+                sh.xds[tid] = P.xd_swap[tid];
             }
             if (tid >= 32 && tid < 32 + FN - 1) {
                 const int l = tid - 32;
@@ -655,7 +685,7 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
                 case 3: disc = path_and_payoff<LEAN, 3>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
                 default: disc = path_and_payoff<LEAN, -1>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
             }
-            if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[sw], FN, FF, t);
+            if (exp_range_left(worst)) disc = generic_trial(params[sw], FN, FF, t);
             sum += disc;                                                  // HSB:203
             sumsq = fma(disc, disc, sumsq);                               // HSB:204
         }
@@ -677,6 +707,8 @@ struct OneSwaption {
     double4 fd[FN - 1];  // {fac0, fac1, fac2} * sqrt_ddelt and pdTotalDrift * ddelt per maturity
     double fwd[FN];
     double pay[FN];
+    double xdp[FN];      // SwParams::xd_path
+    double xds[FN];      // SwParams::xd_swap
     double ddelt, swap_ddelt;
     long long seed, sims, chunk_trials;
     int start, len, last_pay, tpt;
@@ -727,7 +759,7 @@ sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ p
                 case 3: disc = path_and_payoff<LEAN, 3>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
                 default: disc = path_and_payoff<LEAN, -1>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
             }
-            if (worst >= EXP_HI_LIMIT) disc = generic_trial(params[P.sw_index], FN, FF, t);
+            if (exp_range_left(worst)) disc = generic_trial(params[P.sw_index], FN, FF, t);
             sum += disc;                     // HSB:203
             sumsq = fma(disc, disc, sumsq);  // HSB:204
         }

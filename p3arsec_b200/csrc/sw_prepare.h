@@ -66,6 +66,19 @@ inline bool prepare(SwParams &P, const sw_gpu_swaption &s, int iN, int iFactors,
     P.ddelt = ddelt;
     P.sqrt_ddelt = sqrt(ddelt);
     P.swap_ddelt = (double)(dSwapVectorYears / iSwapVectorLength);
+    // Cumulative drift of the path entries the payoff reads (path_and_payoff keeps its rows drift-free): row j of the path is
+    // row j-1 shifted by one maturity plus driftdt (HJM_SimPath_Forward_Blocking), so cd_j[l] = cd_{j-1}[l+1] + driftdt[l],
+    // zero beyond the triangle like the path itself.
+    {
+        double cd[MAXN + 1] = {0};
+        for (int j = 0; j <= iN - 1; ++j) {
+            if (j <= iN - 2) P.xd_path[j] = -cd[0] * ddelt;                       // read by time step j + 1 (HSB:167-172)
+            if (j == iSwapStartTimeIndex)
+                for (int i = 0; i < iN; ++i) P.xd_swap[i] = -cd[i] * P.swap_ddelt;  // read by the swap leg (HSB:184)
+            for (int l = 0; l <= iN - 2 - j; ++l) cd[l] = cd[l + 1] + P.driftdt[l];
+            for (int l = iN - 1 - j < 0 ? 0 : iN - 1 - j; l < iN; ++l) cd[l] = 0;
+        }
+    }
     P.seed = seed;
     P.trials = lTrials;
     P.sims = lTrials <= 0 ? 0 : ((lTrials + BLOCKSIZE - 1) / BLOCKSIZE) * (long long)BLOCKSIZE;   // HSB:156
@@ -85,6 +98,8 @@ inline void to_one_swaption(OneSwaption &P, const SwParams &H)
     for (int l = 0; l < FN; ++l) {
         P.fwd[l] = H.fwd[l];
         P.pay[l] = H.pay[l];
+        P.xdp[l] = H.xd_path[l];
+        P.xds[l] = H.xd_swap[l];
     }
     P.ddelt = H.ddelt;
     P.swap_ddelt = H.swap_ddelt;

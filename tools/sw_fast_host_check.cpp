@@ -32,7 +32,7 @@ static double one_trial(const SRC &src, const double *tab, const double *tail, d
         case 3: disc = path_and_payoff<LEAN, 3>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
         default: disc = path_and_payoff<LEAN, -1>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
     }
-    if (worst >= EXP_HI_LIMIT) {
+    if (exp_range_left(worst)) {
         ++fallbacks;
         disc = generic_trial(P, FN, FF, t);
     }
@@ -64,6 +64,8 @@ int main()
         for (int l = 0; l < FN; ++l) {  // what sw_sim_fast stages into shared memory per work item
             sh.fwd[l] = one.fwd[l];
             sh.pay[l] = one.pay[l];
+            sh.xdp[l] = one.xdp[l];
+            sh.xds[l] = one.xds[l];
             if (l < FN - 1) sh.fd[l] = one.fd[l];
         }
         double sum = 0, sumsq = 0;
