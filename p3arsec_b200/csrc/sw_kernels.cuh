@@ -167,11 +167,10 @@ SW_HD_NOINLINE double cumnormalinv_ieee(double u)
     return x < 0.0 ? -p : p;
 }
 
-// exp for the fast kernel.  exp_core = bsm::exp_f64 without its underflow clamp (11 FP64 operations), valid for
-// |x| < 700; everything else (huge rates, inf, NaN -- reached only after a draw of exactly 0, see the tail pass) goes
-// to libdevice, out of line.  The range check is done on the high word with integer instructions: the FP64 pipe is
+// exp for the fast kernel.  exp_core = bsm::exp_f64 without its underflow clamp and without the second range-reduction step
+// (9 FP64 operations), used for |x| < 2; everything else (rates of several hundred per cent, inf, NaN -- the latter reached
+// only after a draw of exactly 0, see the tail pass) goes to libdevice, out of line, with the whole trial (generic_trial).  The range check is done on the high word with integer instructions: the FP64 pipe is
 // the bottleneck of this kernel and a DSETP would cost it two issue cycles per exponential.
-SW_HD_NOINLINE double exp_slow(double x) { return exp(x); }
 // Where exp_core reads 2^(j/64) from.  The index j is the low six bits of a rounded product, i.e. random per lane, so a
 // plain 64-entry table in shared memory serves a half-warp's 64-bit loads in 2-4 wavefronts (16 bank pairs, 16 lanes
 // with unrelated j).  REP = 16 copies interleaved [j][lane & 15] give every lane of a half-warp its own bank pair
@@ -223,23 +222,23 @@ SW_HD double exp_core(double x, const ET &et)
     double nd = fma(x, kd(K_EXP_INV), MAGIC);
     const int n = (int)(uint32_t)to_bits(nd);  // round(x * 64/ln2) = 64 k + j
     nd -= MAGIC;
-    double r = fma(nd, -kd(K_EXP_HI), x);
-    r = fma(nd, -kd(K_EXP_LO), r);
+    // x - n ln2/64 with the 53-bit constant alone: the FMA rounds once, and what the low part of ln2/64 (3.6e-19) would add is
+    // below 185 * 3.6e-19 = 6.7e-17 for the |x| < 2 this block is used for (EXP_HI_LIMIT) -- a third of an ulp of the result
+    // at the very edge, 1e-17 for the |x| < 0.2 of real rates; bsm::exp_f64 keeps the second step for its |x| < 700.
+    const double r = fma(nd, -kd(K_EXP_HI), x);
     double q = fma(kd(K_EXP_C5), r, kd(K_EXP_C4));
     q = fma(q, r, kd(K_EXP_C3));
     q = fma(q, r, 0.5);
     const double em1 = fma(q, r * r, r);
-    const double T = et.scaled(n);   // 2^k 2^(j/64): normal for |x| < 700, so scaling T first changes no bit of the result
+    const double T = et.scaled(n);   // 2^k 2^(j/64): a normal number, so scaling T first changes no bit of the result
     return fma(T, em1, T);
 }
-// |x| >= 700, inf or NaN <=> (high word of x, sign cleared) >= EXP_HI_LIMIT.  The fast kernel evaluates every
-// exponential with exp_core, branch-free, and only tracks the largest such high word of the trial (LOP3 + VIMNMX on the
-// integer pipes); a trial that exceeded the limit is redone by generic_trial().
+// |x| >= 2, inf or NaN <=> (high word of x, sign cleared) >= EXP_HI_LIMIT.  The fast kernel evaluates every exponential with
+// exp_core, branch-free, and only tracks the high words of the arguments (integer pipes); a trial that exceeded the limit -- a
+// rate above 100 % a year and more, or the inf / NaN that follow a draw of exactly 0 -- is redone by generic_trial().
 // `worst` accumulates the high words with OR (a three-input LOP3 takes two exponentials at a time; a running maximum of the
-// sign-cleared words cost a LOP3 and a VIMNMX each): the OR is >= every word, and words below 0x40000000 (|x| < 2, i.e.
-// every rate below 200 % a year) cannot OR up to the limit, so the test is exact for them and conservative above -- a
-// trial sent to generic_trial() without need is still priced correctly.
-constexpr uint32_t EXP_HI_LIMIT = 0x4085E000u;
+// sign-cleared words cost a LOP3 and a VIMNMX each): the limit is a single bit, so the OR exceeds it iff one word does.
+constexpr uint32_t EXP_HI_LIMIT = 0x40000000u;
 template <class ET>
 SW_HD double exp_tracked(double x, const ET &et, uint32_t &worst)
 {

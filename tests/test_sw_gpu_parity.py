@@ -152,6 +152,25 @@ def test_counters_crossing_the_generator_modulus():
             assert_parity(mean, err, omean, oerr, 64, "seed %d/%s" % (seed, mode))
 
 
+def test_very_high_rates_fall_back_to_the_generic_trial():
+    """The fast kernels' exponential is used for |rate * dt| < 2 (sw_kernels.cuh EXP_HI_LIMIT); trials beyond are redone by
+    generic_trial() inside the same launch.  Yield curves of 60-260 % put the portfolio on both sides of the limit
+    (tests/test_sw_oracle.py checks on the host build that some swaptions never and some always fall back)."""
+    n = 6
+    p = np.zeros(n, dtype=sw.SWAPTION_DTYPE)
+    p["dYears"], p["dStrike"], p["dPaymentInterval"], p["dMaturity"], p["dTenor"] = 11.0, 0.9, 1.0, 1.0, 3.0
+    y = np.tile(np.array([0.6, 1.0, 1.4, 1.8, 2.2, 2.6])[:, None], (1, 11)) + 0.01 * np.arange(11)[None]
+    f = np.tile(sw.FACTOR_TABLE[None] * 4.0, (n, 1, 1))
+    omean, oerr = so.price_map(p, y, f, 99, 2048)
+    for mode, flags in MODES[:2]:
+        mean, err, _, _ = gpu_price(p, y, f, 99, 2048, flags)
+        assert_parity(mean, err, omean, oerr, 2048, "high rates/" + mode)
+    # and through the one-launch-per-swaption kernel
+    mean, err, _, _ = gpu_price(p[:2], y[:2], f[:2], 99, 300000, 0)
+    bmean, berr, _, _ = gpu_price(p[:2], y[:2], f[:2], 99, 300000, sw.FLAG_BATCHED)
+    assert_parity(mean, err, bmean, berr, 300000, "high rates/one-swaption vs batched")
+
+
 def test_negative_and_huge_seeds_fall_back_to_literal_arithmetic():
     _, p, y, f = sw.make_portfolio(3)
     for seed in (-5, -2147483647 * 3, 2**41 + 12345):

@@ -239,6 +239,23 @@ def test_fast_arithmetic_falls_back_when_a_draw_is_zero(fast_host):
     _close(s / 64, omean)
 
 
+def test_fast_arithmetic_hands_very_high_rates_to_the_generic_trial(fast_host):
+    """exp_core is used for |rate * dt| < 2 (one range-reduction step, sw_kernels.cuh EXP_HI_LIMIT); a trial with a larger
+    argument is redone by generic_trial().  Yield curves of 60-260 % with dt = 1 year put the portfolio on both sides of the
+    limit: some swaptions never fall back, some always do, and every price still equals the oracle's."""
+    n = 6
+    p = np.zeros(n, dtype=sw.SWAPTION_DTYPE)
+    p["dYears"], p["dStrike"], p["dPaymentInterval"], p["dMaturity"], p["dTenor"] = 11.0, 0.9, 1.0, 1.0, 3.0
+    y = np.tile(np.array([0.6, 1.0, 1.4, 1.8, 2.2, 2.6])[:, None], (1, 11)) + 0.01 * np.arange(11)[None]
+    f = np.tile(sw.FACTOR_TABLE[None] * 4.0, (n, 1, 1))
+    trials = 512
+    omean, _ = so.price_map(p, y, f, 99, trials)
+    for lean, source in ((0, 0), (0, 1), (1, 1)):
+        s, _, fb = fast_host(p, y, f, 99, trials, lean, source)
+        assert fb[0] == 0 and fb[-1] == trials, fb
+        _close(s / trials, omean)
+
+
 @pytest.mark.parametrize("rng_seed", [1, 2, 3])
 def test_fast_arithmetic_random_portfolios_on_the_host(fast_host, rng_seed):
     """Random contracts beyond what the reference driver creates (compounding conventions, maturities, tenors, payment
