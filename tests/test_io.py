@@ -91,6 +91,17 @@ def test_loader_odd_tokens_fall_back_to_fscanf(tmp_path):
         assert a[k].tobytes() == b[k].tobytes(), k
 
 
+def test_only_capital_p_is_a_put(tmp_path):
+    """blackscholes.c:761: otype = (OptionType == 'P') ? 1 : 0 -- any other character, 'p' included, prices as a call
+    (SURVEY.md appendix A.2).  Fast path of the loader and its fscanf fallback against the oracle's loader."""
+    rows = ["42.00 40.00 0.1000 0.00 0.20 0.50 %s 0.00 4.75" % c for c in "PCpcXx?1"]
+    rows.append("+42.00 4e1 0.1000 0.00 .20 5e-1 p 0.00 4.75")   # odd tokens: the fscanf path
+    path = _write(tmp_path, "%d\n" % len(rows) + "\n".join(rows) + "\n")
+    a, b = host.load_options(path, 4), oracle_lib.load(path, 4)
+    assert b["otype"].tolist() == [1, 0, 0, 0, 0, 0, 0, 0, 0]
+    assert a["otype"].tolist() == b["otype"].tolist()
+
+
 @pytest.mark.parametrize("text", ["", "abc\n", "3\n" + ROW + "\n", "1\n42.00 40.00 0.1000 0.00 0.20 0.50 C 0.00\n",
                                   "1\n42.00 40.00 x 0.00 0.20 0.50 C 0.00 4.7\n"])
 def test_loader_errors_like_reference(tmp_path, text):
