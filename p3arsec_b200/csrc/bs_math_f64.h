@@ -185,7 +185,8 @@ BS_HD double log_f64_t(double x, const LT &lt)
 {
     const uint64_t b = to_bits(x);
     const int i = (int)(b >> 46) & 63;            // top 6 mantissa bits: m in [1 + i/64, 1 + (i+1)/64)
-    const int e = (int)(b >> 52) - 1023 + (i >= LOG_SPLIT ? 1 : 0);
+    // exponent, + 1 from LOG_SPLIT on: adding 64 - LOG_SPLIT to the index bits carries into the exponent field exactly then
+    const int e = (int)(((uint32_t)(b >> 32) + ((64u - LOG_SPLIT) << 14)) >> 20) - 1023;
     const double m = from_bits((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
     double rc, lc;
     lt.pair(i, rc, lc);

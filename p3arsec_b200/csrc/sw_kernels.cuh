@@ -117,6 +117,7 @@ SW_HD double ranunif_literal(long long ctr)
 // +1513517 per draw, and Schrage's step 16807 x mod (2^31 - 1) (exactly what the k1/127773/2836 dance computes
 // for x in [0, 2^31 - 1)) done with one 64-bit product and a Mersenne fold.
 constexpr uint32_t RU_M = 2147483647u;
+constexpr int FD_MAX_DRAWS = 30;  // draws per trial of the fast kernels, (iN - 1) * iFactors = FD below
 SW_HD uint32_t mersenne31(uint64_t p)  // p < 2^62
 {
     uint64_t s = (p & RU_M) + (p >> 31);
@@ -263,9 +264,8 @@ constexpr uint32_t S_LO = 171798692u, S_HI = 1975684955u;
 template <bool TWO_LOGS, class LT>
 SW_HD double tail_normal(uint32_t x0, int k, const LT &lt, const double *tailtab)
 {
-    uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26: one conditional subtraction reduces it
-    xk = xk >= RU_M ? xk - RU_M : xk;
-    const uint32_t s = ru_int(xk);
+    const uint32_t xk = x0 + (uint32_t)k * 1513517u;  // < 2^31 + 2^26, left unreduced: xk * 16807 < 2^46 and ru_int's fold is
+    const uint32_t s = ru_int(xk);                    // below 2 (2^31 - 1), so its one conditional subtraction gives the exact draw
     const double u = (double)(int)s * 4.656612875e-10;
     const bool upper = s > S_HI;
     const double r = upper ? 1.0 - u : u;
@@ -283,8 +283,22 @@ SW_HD double tail_normal(uint32_t x0, int k, const LT &lt, const double *tailtab
     } else {
         p = swt::moro_tail_t(r, lt, tailtab);  // P8(log(-log r)): one logarithm + the composite table (sw_tail.h)
     }
-    p = s == 0 ? INFINITY : p;
-    return upper ? p : -p;
+    // (a draw of exactly 0 -- log(-log 0) = +inf in the reference -- never gets here with a meaning: trial_draws_zero() sends
+    // such a trial to generic_trial() as a whole; what this function returns for it is finite garbage.)
+    // sign: -p for the lower tail.  S_HI - s is negative exactly for the upper tail (both below 2^31): its sign bit cancels the flip.
+    return bsm::from_bits(bsm::to_bits(p) ^ ((uint64_t)(~(S_HI - s) & 0x80000000u) << 32));
+}
+
+// Does one of the trial's FD draws come out as exactly 0?  Draw k is 0 iff its residue x0 + k c is a multiple of 2^31 - 1
+// (c = 1513517, x0 = ru_residue(first counter) in [0, 2^31 - 1)), i.e. iff 2^31 - 1 - x0 (or x0 itself, for k = 0) is one of the
+// first FD multiples of c: a range test that fails for 98 % of the trials, then one remainder.  The reference carries the
+// resulting -inf through the path; the fast kernels hand the whole trial to generic_trial(), once per trial instead of a
+// compare and a 64-bit select per tail draw.
+SW_HD bool trial_draws_zero(uint32_t x0)
+{
+    const uint32_t d = x0 == 0 ? 0u : RU_M - x0;
+    if (d > (uint32_t)(FD_MAX_DRAWS - 1) * 1513517u) return false;
+    return d % 1513517u == 0;
 }
 
 #if defined(__CUDACC__)
@@ -384,6 +398,7 @@ SW_HD_NOINLINE double generic_trial(const SwParams &P, int iN, int nF, long long
 // sw_sim_fast: iN = 11, iFactors = 3 (the only shape the reference drivers create: HJM_Securities.cpp:56,58).
 // =====================================================================================================================
 constexpr int FN = 11, FF = 3, FD = (FN - 1) * FF;
+static_assert(FD == FD_MAX_DRAWS, "trial_draws_zero() covers the draws of one trial");
 
 struct FastShared {
     double tail[swt::TAIL_DOUBLES];  // composite table of Moro's tail branch (5 KB; rows of 80 B, 16-byte aligned)
@@ -672,11 +687,12 @@ sw_sim_fast(const SwParams *__restrict__ params, const Geom g, double2 *__restri
             if (t >= sims) break;
 
             // ---- phase A + tail pass: the trial's normals into sh.z (see normals())
-            normals<LEAN>(lt, sh.tail, z, tid, ru_residue(seed + t * FD), steps);
+            const uint32_t x0 = ru_residue(seed + t * FD);
+            normals<LEAN>(lt, sh.tail, z, tid, x0, steps);
 
             // ---- phase B: path, discount factors, payoff; specialised on the swap start index (1..3 covers every
             // swaption the reference drivers create: dMaturity = 1, dYears in [5, 20))
-            uint32_t worst = 0;
+            uint32_t worst = trial_draws_zero(x0) ? EXP_HI_LIMIT : 0u;
             double disc;
             switch (start) {
                 case 1: disc = path_and_payoff<LEAN, 1>(sh, et, z, tid, ddelt, swap_ddelt, start, swap_end, worst); break;
@@ -749,8 +765,9 @@ sw_sim_one(const __grid_constant__ OneSwaption P, const SwParams *__restrict__ p
         for (int m = 0; m < P.tpt; ++m) {
             const long long t = (long long)chunk * P.chunk_trials + (long long)m * THREADS + tid;
             if (t >= P.sims) break;
-            normals<LEAN>(lt, sh.tail, z, tid, ru_residue(P.seed + t * FD), steps);
-            uint32_t worst = 0;
+            const uint32_t x0 = ru_residue(P.seed + t * FD);
+            normals<LEAN>(lt, sh.tail, z, tid, x0, steps);
+            uint32_t worst = trial_draws_zero(x0) ? EXP_HI_LIMIT : 0u;
             double disc;
             switch (P.start) {
                 case 1: disc = path_and_payoff<LEAN, 1>(P, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;

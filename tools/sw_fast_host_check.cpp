@@ -22,9 +22,10 @@ static double one_trial(const SRC &src, const double *tab, const double *tail, d
     const int steps = LEAN ? P.start : FN - 1;
     const int swap_end = LEAN ? P.last_pay : P.len - 1;
     const bsm::PlainLogTab plt = {tab};
-    normals<LEAN>(plt, tail, z, tid, ru_residue(P.seed + t * FD), steps);
+    const uint32_t x0 = ru_residue(P.seed + t * FD);
+    normals<LEAN>(plt, tail, z, tid, x0, steps);
     const ExpTab<0> et = {tab + bsm::TAB_EXP, 0};  // the plain table: bank layout is a device-only concern
-    uint32_t worst = 0;
+    uint32_t worst = trial_draws_zero(x0) ? EXP_HI_LIMIT : 0u;
     double disc;
     switch (P.start) {
         case 1: disc = path_and_payoff<LEAN, 1>(src, et, z, tid, P.ddelt, P.swap_ddelt, P.start, swap_end, worst); break;
