@@ -69,6 +69,28 @@ __device__ __forceinline__ int2 ld_stream(const int2 *p)
     asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
+// The same loads under a predicate (the destination keeps its value when `on` is false): the software-pipelined loop issues
+// the next trip's loads without a branch, so they stay where the program puts them -- ahead of the current trip's math.
+__device__ __forceinline__ void ld_stream_if(float4 &r, const float4 *p, int on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w) : "l"(p), "r"(on));
+}
+__device__ __forceinline__ void ld_stream_if(int4 &r, const int4 *p, int on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"(on));
+}
+__device__ __forceinline__ void ld_stream_if(double2 &r, const double2 *p, int on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n\t}"
+                 : "+d"(r.x), "+d"(r.y) : "l"(p), "r"(on));
+}
+__device__ __forceinline__ void ld_stream_if(int2 &r, const int2 *p, int on)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];\n\t}"
+                 : "+r"(r.x), "+r"(r.y) : "l"(p), "r"(on));
+}
 __device__ __forceinline__ void st_stream(float4 *p, float4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
@@ -524,14 +546,31 @@ __global__ void __launch_bounds__(256) bs_map(Streams<FP> a, size_t n, ErrChk ec
         const size_t step = (size_t)UNROLL * stride;
         load_trip(bufA, g);
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        // The next trip's loads are predicated, not branched around: with a conditional block the compiler scheduled the
+        // current trip's math ahead of it once the fp64 math had shrunk, and the loads lost 150 instructions of head start.
+        auto load_trip_if = [&](Group<FP> *dst, size_t g0, bool on) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const size_t gi = g0 + u * stride;
+                const int p = (on && (u == 0 || gi < groups)) ? 1 : 0;
+                const size_t gs = p ? gi : 0;  // a predicated-off load still forms its address
+                ld_stream_if(dst[u].s, p_s + gs, p);
+                ld_stream_if(dst[u].k, p_k + gs, p);
+                ld_stream_if(dst[u].r, p_r + gs, p);
+                ld_stream_if(dst[u].v, p_v + gs, p);
+                ld_stream_if(dst[u].t, p_t + gs, p);
+                ld_stream_if(dst[u].o, p_o + gs, p);
+                if (CHK) ld_stream_if(dst[u].ref, p_ref + gs, p);
+            }
+        };
         for (;;) {
             bool more = g + step < groups;
-            if (more) load_trip(bufB, g + step);  // in flight while trip A is priced
+            load_trip_if(bufB, g + step, more);  // in flight while trip A is priced
             price_trip(bufA, g);
             if (!more) break;
             g += step;
             more = g + step < groups;
-            if (more) load_trip(bufA, g + step);  // in flight while trip B is priced
+            load_trip_if(bufA, g + step, more);  // in flight while trip B is priced
             price_trip(bufB, g);
             if (!more) break;
             g += step;
