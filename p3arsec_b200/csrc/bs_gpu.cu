@@ -1106,13 +1106,15 @@ int bs_gpu_init_ex(bs_gpu_ctx **out, const bs_gpu_config *cfg)
     // options, 1.98 -> 1.69 at 64K; from 256K options on it costs time, as it does for the large sets).
     if (c->n / (size_t)cfg->num_gpus <= ((size_t)128 << 10) && !cfg->variant) c->flags |= BS_GPU_FLAG_PDL;
     {
-        // Shape of the fp64 TMA kernel.  Shards of a million options and more take shape 2 (two groups per consumer thread and
-        // tile: the per-tile overhead -- barrier wait, addresses, loop -- is paid once per four options): measured +1-3 % in
-        // the sustained, power-capped regime every bench line lives in (120.9-121.5 against 117.8-120.5 G options/s on one
-        // board, 112.1-112.8 against 110.9-111.1 on another; bursts of a few ms are equal), profiles/r02_tune_fp64_gtab.txt.
+        // Shape of the fp64 TMA kernel: 0 (16 consumer warps, one group per thread and tile, four stages).  While the kernel
+        // executed 162 instructions per option, shape 2 (two groups per consumer thread and tile: barrier wait, addresses and
+        // loop paid once per four options) was worth 1-3 % in the sustained, power-capped regime every bench line lives in
+        // and was the default for shards of a million options and more (profiles/r02_tune_fp64_gtab.txt); at 141 instructions
+        // per option the order is the other way round -- 118.6-118.9 (shape 0) / 117.1-118.2 (1) / 116.1-117.4 (2) G options/s,
+        // three alternating bench lines on one board, profiles/r02_tune_fp64_shapes_final.txt.
         // BS_GPU_TMA_WIDE = 0 | 1 | 2 forces a shape (measurements, tests).
         const char *w = getenv("BS_GPU_TMA_WIDE");
-        if (c->fp_bytes == 8) c->tma_shape = (w && *w >= '0' && *w <= '2') ? *w - '0' : (c->n / (size_t)cfg->num_gpus >= ((size_t)1 << 20) ? 2 : 0);
+        if (c->fp_bytes == 8) c->tma_shape = (w && *w >= '0' && *w <= '2') ? *w - '0' : 0;
     }
     // fp64 (unless the caller chose a geometry/variant explicitly): the fast-math kernel takes its inputs through the
     // bulk-copy ring (bs_map_tma: 81.0 us per 10M options = 6.42 TB/s against 85.9 us with software-pipelined LDG.128

@@ -129,8 +129,8 @@ def test_tma_variant_sizes(n, fp_bytes):
 @pytest.mark.parametrize("shape", ["0", "1", "2"])
 @pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 300007, 3_000_001])
 def test_tma_shapes_fp64(n, shape, monkeypatch):
-    # the three shapes of the fp64 ring kernel (tile 1024 / 1536 / 2048 options; the library picks 2 for shards of >= 1M
-    # options and 0 below; BS_GPU_TMA_WIDE forces one): each bit-identical to the LDG kernel, whole tiles and remainder
+    # the three shapes of the fp64 ring kernel (tile 1024 / 1536 / 2048 options; the library picks 0, BS_GPU_TMA_WIDE forces
+    # one): each bit-identical to the LDG kernel, whole tiles and remainder
     inputs = inputgen_like(n, seed=n + 7, dtype=np.float64)
     base, _, _ = gpu_prices(inputs, 8, num_runs=2, variant=1)
     monkeypatch.setenv("BS_GPU_TMA_WIDE", shape)
