@@ -24,7 +24,7 @@
  *                      for the full kernel when a swaption has enough trials to fill the GPU.
  *   sw_sim_generic     any shape, the reference's operation order (generic_trial), also the out-of-range fallback.
  *   sw_finalize        partial sums -> mean and standard error.
- * Building blocks: normals() = phase A (30 central-branch CumNormalInv, staged six at a time) + the deferred tail pass
+ * Building blocks: normals() = phase A (30 central-branch CumNormalInv, staged three at a time) + the deferred tail pass
  * (Moro's tail branch only for the draws that need it, through the composite table of sw_tail.h);
  * path_and_payoff<LEAN, START> = phase B, specialised on the swap start index.  DESIGN.md section 9 has the numbers.
  */
@@ -433,11 +433,14 @@ SW_HOST_DEVICE constexpr size_t fast_shared_bytes(int z_rows) { return sizeof(Fa
 #endif
 #ifndef SW_PAIRED_RCP
 #define SW_PAIRED_RCP 0  /* 1: phase A shares one reciprocal (one MUFU seed + Newton step) per pair of central draws.  Measured
-                            neutral on B200 (12.56-12.62 against 12.62 G trials/s native: 15 MUFU.RCP64H fewer per trial, the same
-                            FP64 count, the same time -- the seeds were not what the dispatch port was waiting for), so off. */
+                            neutral on B200 in the first half of round 2 (12.56-12.62 against 12.62 G trials/s native: 15 MUFU.RCP64H
+                            fewer per trial, the same FP64 count, the same time -- the seeds were not what the dispatch port was
+                            waiting for) and 2.5 % slower with the final kernel (13.37 against 13.71), so off. */
 #endif
 #ifndef SW_PHASE_A_GROUP
-#define SW_PHASE_A_GROUP 6  /* draws evaluated side by side in phase A: 3, 6, 10, 15 or 30 */
+#define SW_PHASE_A_GROUP 3  /* draws evaluated side by side in phase A: 3, 6, 10, 15 or 30.  Measured with the final kernel on one board,
+                               alternating (profiles/r02_sw_tune_driftfree.txt): 13.84 (3) / 13.71 (6) / 13.72 (10) / 12.38 (15, spills)
+                               G trials/s; round 1 had 3 / 6 / 10 within noise of each other. */
 #endif
 constexpr int TAIL_TRIP = SW_TAIL_TRIP;
 
