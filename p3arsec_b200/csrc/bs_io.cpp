@@ -159,6 +159,47 @@ template <typename FP> inline bool parse_fp(const char *b, const char *e, FP *ou
     return true;
 }
 
+// The common case in one pass over the token: a plain decimal [-]ddd[.ddd] of at most 19 digits, terminated by white space
+// (or the end of the file), converted by Clinger's exact division as in parse_fp.  Returns 1 with *end behind the token, or
+// 0 for anything else -- exponents, hex floats, inf, more digits than one division can take, over-long tokens -- which the
+// caller hands to parse_fp (same result for the tokens both accept: this is its fast path without the second scan).
+template <typename FP> inline int parse_plain(const char *buf, size_t p, size_t hi, FP *out, size_t *end)
+{
+    const size_t lim = std::min(hi, p + 40);
+    size_t q = p;
+    const bool neg = buf[q] == '-';
+    q += neg;
+    uint64_t m = 0;
+    const size_t d0 = q;
+    for (; q < lim; q++) {
+        const unsigned d = (unsigned)(buf[q] - '0');
+        if (d > 9) break;
+        m = m * 10 + d;
+    }
+    const size_t int_digits = q - d0;
+    size_t frac = 0;
+    if (q < lim && buf[q] == '.') {
+        const size_t f0 = ++q;
+        for (; q < lim; q++) {
+            const unsigned d = (unsigned)(buf[q] - '0');
+            if (d > 9) break;
+            m = m * 10 + d;
+        }
+        frac = q - f0;
+    }
+    const size_t digits = int_digits + frac;
+    if (q < hi && !is_space(buf[q])) return 0;  // not plain, or cut off by the 40-byte window
+    if (digits == 0 || int_digits > 30) return 0;
+    *end = q;
+    if (!out) return 1;  // an unwanted column (e.g. the 20-digit DGrefval of a build without ERR_CHK): syntax only
+    const uint64_t exact_limit = sizeof(FP) == 4 ? (1ull << 24) : (1ull << 53);
+    const size_t pow_limit = sizeof(FP) == 4 ? 10 : 22;
+    if (digits > 19 || m >= exact_limit || frac > pow_limit) return 0;
+    const FP v = (FP)m / (FP)POW10[frac];
+    *out = neg ? -v : v;
+    return 1;
+}
+
 template <typename FP>
 int load_fast(const bs_io_file *f, size_t count, const Dest<FP> &dst, int nthreads)
 {
@@ -192,21 +233,27 @@ int load_fast(const bs_io_file *f, size_t count, const Dest<FP> &dst, int nthrea
         // skip the tail of a token that started in the previous range
         if (p > lo && !is_space(buf[p - 1]))
             while (p < end && !is_space(buf[p])) p++;
+        size_t row = tok / 9;
+        int field = (int)(tok % 9);
         while (p < end && tok < want_tokens) {
             while (p < end && is_space(buf[p])) p++;
             if (p >= end) break;
-            size_t q = p;
-            while (q < hi && !is_space(buf[q])) q++;  // may run into the next range: the token is ours
-            const size_t row = tok / 9;
-            const int field = (int)(tok % 9);
+            // (a token may run into the next range: it is ours)
+            size_t q;
             if (field == 6) {
-                if (q - p != 1) { bad[t] = 1; return; }
+                q = p + 1;
+                if (q < hi && !is_space(buf[q])) { bad[t] = 1; return; }
                 dst.otype[row] = (buf[p] == 'P') ? 1 : 0;  // blackscholes.c:761
             } else {
                 FP *slot = dst.f[field] ? dst.f[field] + row : nullptr;
-                if (!parse_fp<FP>(buf + p, buf + q, slot)) { bad[t] = 1; return; }
+                if (!parse_plain<FP>(buf, p, hi, slot, &q)) {
+                    q = p;
+                    while (q < hi && !is_space(buf[q])) q++;
+                    if (!parse_fp<FP>(buf + p, buf + q, slot)) { bad[t] = 1; return; }
+                }
             }
             tok++;
+            if (++field == 9) { field = 0; row++; }
             p = q;
         }
     });

@@ -49,6 +49,53 @@ def test_loader_large_parallel(tmp_path):
         assert a[k].tobytes() == b[k].tobytes(), k
 
 
+@pytest.mark.parametrize("fp_bytes", [4, 8])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_loader_random_tokens_bit_identical_to_fscanf(tmp_path, fp_bytes, seed):
+    """Differential test of the token parser against fscanf (the oracle's loader): numbers of 1-25 digits with and without
+    a fractional part, signs, leading zeros, trailing dots, tokens longer than the fast path's window, exponent and hex
+    spellings, random white space -- on every thread count, so that byte-range boundaries fall inside tokens."""
+    rng = np.random.RandomState(seed)
+
+    def number():
+        kind = rng.randint(0, 12)
+        nint, nfrac = int(rng.randint(0, 9)), int(rng.randint(0, 9))
+        if kind == 0:
+            nint, nfrac = int(rng.randint(1, 26)), int(rng.randint(0, 26))     # more digits than one exact division takes
+        elif kind == 1:
+            nint, nfrac = int(rng.randint(31, 45)), 0                            # longer than the fast path's window
+        ip = "".join(str(d) for d in rng.randint(0, 10, nint))
+        fp = "".join(str(d) for d in rng.randint(0, 10, nfrac))
+        if kind == 2:
+            ip = "000" + ip
+        tok = ip + ("." + fp if (nfrac or rng.rand() < 0.2) else "")
+        if not any(ch.isdigit() for ch in tok):
+            tok = "0" + tok
+        if kind == 3:
+            tok += "e%d" % rng.randint(-12, 12)
+        if kind == 4:
+            tok = "0x1.%xp%d" % (rng.randint(0, 1 << 20), rng.randint(-8, 8))
+        if rng.rand() < 0.15:
+            tok = "-" + tok
+        elif kind == 5:
+            tok = "+" + tok
+        return tok
+
+    n = 3000
+    seps = [" ", "  ", "\t", " \t ", "\n"]
+    rows = []
+    for _ in range(n):
+        toks = [number() for _ in range(6)] + [rng.choice(list("PCpx"))] + [number(), number()]
+        rows.append("".join(t + seps[rng.randint(0, len(seps))] for t in toks))
+    path = _write(tmp_path, "%d\n" % n + "\n".join(rows) + "\n")
+    b = oracle_lib.load(path, fp_bytes)
+    for nthreads in (1, 3, 8):
+        a = host.load_options(path, fp_bytes, nthreads=nthreads)
+        assert a["numOptions"] == n
+        for k in KEYS:
+            assert a[k].tobytes() == b[k].tobytes(), (k, nthreads)
+
+
 def _write(tmp_path, text):
     p = tmp_path / "in.txt"
     p.write_text(text)
