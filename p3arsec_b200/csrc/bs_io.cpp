@@ -370,7 +370,8 @@ int bs_io_open(const char *path, bs_io_file **file, long long *num_options)
         void *m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (m == MAP_FAILED) { close(fd); delete f; return BS_IO_ERR_OPEN; }
         f->data = (const char *)m;
-        madvise(m, f->size, MADV_SEQUENTIAL | MADV_WILLNEED);
+        madvise(m, f->size, MADV_WILLNEED);    // advice values are not flags: one call each
+        madvise(m, f->size, MADV_SEQUENTIAL);
     }
     if (f->size >= sizeof(SoaHeader) && memcmp(f->data, SOA_MAGIC, 8) == 0) {
         SoaHeader h;
