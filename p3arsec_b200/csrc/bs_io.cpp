@@ -169,6 +169,21 @@ template <typename FP> inline int parse_plain(const char *buf, size_t p, size_t 
     size_t q = p;
     const bool neg = buf[q] == '-';
     q += neg;
+    if (!out) {  // an unwanted column (divq, divs, the 20-digit DGrefval of a build without ERR_CHK): syntax only, no value
+        const size_t d0 = q;
+        while (q < lim && (unsigned)(buf[q] - '0') <= 9) q++;
+        const size_t int_digits = q - d0;
+        size_t frac = 0;
+        if (q < lim && buf[q] == '.') {
+            const size_t f0 = ++q;
+            while (q < lim && (unsigned)(buf[q] - '0') <= 9) q++;
+            frac = q - f0;
+        }
+        if (q < hi && !is_space(buf[q])) return 0;
+        if (int_digits + frac == 0 || int_digits > 30) return 0;
+        *end = q;
+        return 1;
+    }
     uint64_t m = 0;
     const size_t d0 = q;
     for (; q < lim; q++) {
@@ -191,7 +206,6 @@ template <typename FP> inline int parse_plain(const char *buf, size_t p, size_t 
     if (q < hi && !is_space(buf[q])) return 0;  // not plain, or cut off by the 40-byte window
     if (digits == 0 || int_digits > 30) return 0;
     *end = q;
-    if (!out) return 1;  // an unwanted column (e.g. the 20-digit DGrefval of a build without ERR_CHK): syntax only
     const uint64_t exact_limit = sizeof(FP) == 4 ? (1ull << 24) : (1ull << 53);
     const size_t pow_limit = sizeof(FP) == 4 ? 10 : 22;
     if (digits > 19 || m >= exact_limit || frac > pow_limit) return 0;
